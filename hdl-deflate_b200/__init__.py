@@ -1,0 +1,204 @@
+"""hdl-deflate_b200 — B200-native deflate engine behind the HDL-deflate interface.
+
+Host side of the hot path only:
+  * `Engine`      thin object over the C ABI of include/hdlz.h (ctypes, libhdlz.so);
+  * `dropin/`     `deflate` + `myhdl` modules with the reference's names, so the
+                  reference's own test bench drives the GPU engine
+                  (put hdl-deflate_b200/dropin on PYTHONPATH);
+  * `workload`    the synthetic block generator of the benchmark configs.
+
+The compute lives in csrc/*.cu (sm_100a).  There is no CPU implementation in this
+package: without libhdlz.so or without a GPU every call raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from . import workload  # noqa: F401
+
+# constants of the reference module (deflate.py:18, 56-89) at the BASELINE sizes
+IDLE, WRITE, READ, STARTC, STARTD = range(5)
+CWINDOW = 32
+IBSIZE = 2048
+OBSIZE = 32768
+LMAX = 24
+MIN_INPUT = 5
+
+F_VERIFY_HEADER = 1
+F_VERIFY_ADLER = 2
+
+STATUS_NAMES = ("OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR", "TRUNCATED",
+                "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER")
+
+# the message the reference raises for the condition (deflate.py:721, 1140, 1508, 1539, 1560)
+REFERENCE_MESSAGES = {
+    1: "input shorter than 5 bytes: the engine never starts (isize < 4)",
+    2: "Bad method",
+    3: "Invalid data",
+    4: "distance too big",
+    5: "NO EOF!",
+    6: "output buffer too small",
+    7: "Invalid data",
+    8: "unexpected mode",
+    9: "Invalid data",
+}
+
+
+class HdlzError(RuntimeError):
+    """A C-ABI call failed (negative hdlz_error)."""
+
+
+class StreamError(ValueError):
+    """A stream finished with a non-zero hdlz_status."""
+
+    def __init__(self, status):
+        self.status = int(status)
+        name = STATUS_NAMES[self.status] if self.status < len(STATUS_NAMES) else "UNKNOWN"
+        ValueError.__init__(self, "%s (%s)" % (REFERENCE_MESSAGES.get(self.status, "error"), name))
+
+
+def compress_bound(n):
+    return int(_native.load().hdlz_compress_bound(int(n)))
+
+
+def _ptr(a):
+    """Device/host address of a numpy array, torch tensor or raw int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    return int(a.ctypes.data)
+
+
+class Engine(object):
+    """One hdlz context (one GPU).  Mirrors one instantiated `deflate()` block."""
+
+    def __init__(self, device=0):
+        self._lib = _native.load()
+        self._ctx = ctypes.c_void_p()
+        self.device = int(device)
+        self._check(self._lib.hdlz_create(self.device, ctypes.byref(self._ctx)))
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.hdlz_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HdlzError("hdlz error %d: %s" % (rc, self._lib.hdlz_last_error().decode("utf-8", "replace")))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hdlz_launch_count(self._ctx))
+
+    # ---- one stream: a STARTC / STARTD job ---------------------------------------------
+    def compress(self, data):
+        """zlib stream of `data`, bit-identical to the reference's FAST+MATCH10 output."""
+        data = bytes(data)
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
+        cap = compress_bound(len(data))
+        out = np.empty(cap, dtype=np.uint8)
+        n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._check(self._lib.hdlz_compress_stream(self._ctx, src.ctypes.data, len(data), out.ctypes.data, cap,
+                                                   ctypes.byref(n), ctypes.byref(st)))
+        if st.value:
+            raise StreamError(st.value)
+        return out[:n.value].tobytes()
+
+    def decompress(self, data, max_out=None, flags=0):
+        """Inflate one zlib stream.  `max_out=None` grows the buffer until it fits (< 2^LMAX)."""
+        data = bytes(data)
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
+        cap = int(max_out) if max_out is not None else max(1 << 16, 8 * len(data))
+        while True:
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+            n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
+            self._check(self._lib.hdlz_decompress_stream(self._ctx, src.ctypes.data, len(data), out.ctypes.data, cap,
+                                                         ctypes.byref(n), ctypes.byref(st), flags))
+            if st.value == 6 and max_out is None and cap < (1 << LMAX):
+                cap = min(cap * 4, 1 << LMAX)
+                continue
+            if st.value:
+                raise StreamError(st.value)
+            return out[:n.value].tobytes()
+
+    # ---- batches in HOST memory (numpy) --------------------------------------------------
+    def compress_host(self, blocks, lens=None, out_stride=None):
+        """blocks: uint8 [n, in_stride] (C-contiguous, in_stride % 16 == 0).
+        -> (out uint8 [n, out_stride], out_len uint32 [n], status uint32 [n])."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+        n, in_stride = blocks.shape
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, dtype=np.uint32)
+            maxlen = int(lens.max()) if n else 0
+        else:
+            maxlen = in_stride
+        if out_stride is None:
+            out_stride = compress_bound(maxlen)
+        out = np.empty((n, out_stride), dtype=np.uint8)
+        out_len = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.hdlz_compress_host(self._ctx, _ptr(blocks), in_stride, _ptr(lens), in_stride,
+                                                 _ptr(out), out_stride, _ptr(out_len), _ptr(status), n))
+        return out, out_len, status
+
+    def decompress_host(self, data, in_len, out_cap, in_off=None, in_stride=0, out_stride=None, flags=0):
+        """data: uint8 buffer holding the streams (packed with in_off, or [n, in_stride]).
+        -> (out uint8 [n, out_stride], out_len, status)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        in_len = np.ascontiguousarray(in_len, dtype=np.uint32)
+        n = len(in_len)
+        if in_off is not None:
+            in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        elif data.ndim == 2:
+            in_stride = data.shape[1]
+        if out_stride is None:
+            out_stride = (int(out_cap) + 15) & ~15
+        out = np.empty((n, out_stride), dtype=np.uint8)
+        out_len = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.hdlz_decompress_host(self._ctx, _ptr(data), _ptr(in_off), in_stride, _ptr(in_len),
+                                                   _ptr(out), out_stride, int(out_cap), _ptr(out_len), _ptr(status),
+                                                   n, flags))
+        return out, out_len, status
+
+    # ---- batches in DEVICE memory (pointers or torch tensors; asynchronous on `stream`) ----
+    def compress_batch(self, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n,
+                       stream=0):
+        self._check(self._lib.hdlz_compress_batch(self._ctx, _ptr(d_in), in_stride, _ptr(d_in_len), uniform_len,
+                                                  _ptr(d_out), out_stride, _ptr(d_out_len), _ptr(d_status), n,
+                                                  stream or None))
+
+    def decompress_batch(self, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status,
+                         n, flags=0, stream=0):
+        self._check(self._lib.hdlz_decompress_batch(self._ctx, _ptr(d_in), _ptr(d_in_off), in_stride, _ptr(d_in_len),
+                                                    _ptr(d_out), out_stride, out_cap, _ptr(d_out_len), _ptr(d_status),
+                                                    n, flags, stream or None))
+
+    def generate_blocks(self, d_out, stride, length, n, seed=workload.DEFAULT_SEED, first_block=0, stream=0):
+        self._check(self._lib.hdlz_generate_blocks(self._ctx, _ptr(d_out), stride, length, n, seed, first_block,
+                                                   stream or None))
+
+    def sync(self, stream=0):
+        self._check(self._lib.hdlz_stream_sync(self._ctx, stream or None))
+
+
+_default_engine = None
+
+
+def default_engine():
+    """Process-wide engine on cuda:0 (what the drop-in `deflate` module uses)."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine

@@ -1,0 +1,360 @@
+// hdlz_api.cu — the extern "C" surface declared in include/hdlz.h: contexts, argument
+// checking, host-buffer entry points, device-memory helpers.  No CPU codec lives here:
+// every compute entry point ends in a kernel launch or fails.
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "hdlz_common.cuh"
+
+namespace hdlz {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    const int code = (e == cudaErrorMemoryAllocation) ? HDLZ_ERR_NOMEM
+                     : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? HDLZ_ERR_NODEVICE
+                                                                                    : HDLZ_ERR_CUDA;
+    return set_error(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+static int grow(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return HDLZ_SUCCESS;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 4096;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(p, need);
+        want = need;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+    *cap = want;
+    return HDLZ_SUCCESS;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_ctx(hdlz_ctx *ctx)
+{
+    if (!ctx) return set_error(HDLZ_ERR_INVALID, "null context");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return HDLZ_SUCCESS;
+}
+
+}  // namespace hdlz
+
+using namespace hdlz;
+
+extern "C" {
+
+int hdlz_version(void) { return HDLZ_VERSION; }
+
+const char *hdlz_last_error(void) { return g_err; }
+
+const char *hdlz_status_name(uint32_t s)
+{
+    static const char *names[] = {"OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR",
+                                  "TRUNCATED", "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER"};
+    return s < sizeof(names) / sizeof(names[0]) ? names[s] : "UNKNOWN";
+}
+
+int hdlz_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDeviceCount");
+        return 0;
+    }
+    return n;
+}
+
+int hdlz_create(int device, hdlz_ctx **out)
+{
+    if (!out) return set_error(HDLZ_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n == 0) return set_error(HDLZ_ERR_NODEVICE, "no CUDA device");
+    if (device < 0 || device >= n) return set_error(HDLZ_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    HDLZ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HDLZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_error(HDLZ_ERR_NODEVICE, "device %d is sm_%d%d; libhdlz is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    hdlz_ctx *c = new hdlz_ctx();
+    memset(c, 0, sizeof *c);
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    *out = c;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_destroy(hdlz_ctx *c)
+{
+    if (!c) return HDLZ_SUCCESS;
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    if (c->d_in) cudaFree(c->d_in);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->d_meta) cudaFree(c->d_meta);
+    if (c->d_off) cudaFree(c->d_off);
+    delete c;
+    return HDLZ_SUCCESS;
+}
+
+uint32_t hdlz_compress_bound(uint32_t len) { return compress_bound(len); }
+
+int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                        uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
+                        uint32_t *d_status, uint64_t n, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n == 0) return HDLZ_SUCCESS;
+    if (!d_in || !d_out || !d_out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (!aligned16(d_in) || !aligned16(d_out) || (in_stride & 15) || (out_stride & 15))
+        return set_error(HDLZ_ERR_INVALID, "d_in/d_out must be 16-byte aligned and strides multiples of 16");
+    if (!d_in_len && (uniform_len > in_stride || uniform_len >= (1u << HDLZ_LMAX)))
+        return set_error(HDLZ_ERR_INVALID, "uniform_len %u does not fit in_stride / LMAX", uniform_len);
+    return launch_compress(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n,
+                           (cudaStream_t)stream);
+}
+
+int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
+                          const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
+                          uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n == 0) return HDLZ_SUCCESS;
+    if (!d_in || !d_in_len || !d_out || !d_out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (out_cap > out_stride) return set_error(HDLZ_ERR_INVALID, "out_cap exceeds out_stride");
+    if ((reinterpret_cast<uintptr_t>(d_in) & 3u))
+        return set_error(HDLZ_ERR_INVALID, "d_in must be 4-byte aligned");
+    return launch_inflate(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n,
+                          flags, (cudaStream_t)stream);
+}
+
+int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
+                       uint32_t uniform_len, uint8_t *out, uint64_t out_stride, uint32_t *out_len,
+                       uint32_t *status, uint64_t n)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n == 0) return HDLZ_SUCCESS;
+    if (!in || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if ((in_stride & 15) || (out_stride & 15)) return set_error(HDLZ_ERR_INVALID, "strides must be multiples of 16");
+    const size_t in_bytes = (size_t)n * in_stride, out_bytes = (size_t)n * out_stride;
+    if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;
+    if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_bytes))) return rc;
+    if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
+    uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
+    cudaStream_t s = ctx->stream;
+    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
+    if (in_len) HDLZ_CUDA(cudaMemcpyAsync(d_len, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    rc = hdlz_compress_batch(ctx, ctx->d_in, in_stride, in_len ? d_len : nullptr, uniform_len, ctx->d_out, out_stride,
+                             d_olen, d_st, n, s);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaMemcpyAsync(out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaMemcpyAsync(out_len, d_olen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (status) HDLZ_CUDA(cudaMemcpyAsync(status, d_st, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaStreamSynchronize(s));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint64_t in_stride,
+                         const uint32_t *in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
+                         uint32_t *out_len, uint32_t *status, uint64_t n, uint32_t flags)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n == 0) return HDLZ_SUCCESS;
+    if (!in || !in_len || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    size_t in_bytes;
+    if (in_off) {
+        in_bytes = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            const size_t e = (size_t)in_off[i] + in_len[i];
+            if (e > in_bytes) in_bytes = e;
+        }
+    } else {
+        in_bytes = (size_t)n * in_stride;
+    }
+    const size_t out_bytes = (size_t)n * out_stride;
+    if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, in_bytes + 16))) return rc;
+    if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_bytes))) return rc;
+    if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
+    if (in_off && (rc = grow((void **)&ctx->d_off, &ctx->d_off_cap, n * sizeof(uint64_t)))) return rc;
+    uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
+    cudaStream_t s = ctx->stream;
+    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
+    HDLZ_CUDA(cudaMemcpyAsync(d_len, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (in_off) HDLZ_CUDA(cudaMemcpyAsync(ctx->d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    rc = hdlz_decompress_batch(ctx, ctx->d_in, in_off ? ctx->d_off : nullptr, in_stride, d_len, ctx->d_out, out_stride,
+                               out_cap, d_olen, d_st, n, flags, s);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaMemcpyAsync(out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaMemcpyAsync(out_len, d_olen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (status) HDLZ_CUDA(cudaMemcpyAsync(status, d_st, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaStreamSynchronize(s));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                         uint32_t *out_len, uint32_t *status)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!in || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
+    *out_len = 0;
+    const size_t in_slot = ((size_t)len + 15) & ~(size_t)15;
+    const size_t out_slot = compress_bound(len);
+    if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, in_slot + 16))) return rc;
+    if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_slot))) return rc;
+    if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * sizeof(uint32_t)))) return rc;
+    cudaStream_t s = ctx->stream;
+    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, len, cudaMemcpyHostToDevice, s));
+    rc = hdlz_compress_batch(ctx, ctx->d_in, in_slot ? in_slot : 16, nullptr, len, ctx->d_out, out_slot, ctx->d_meta + 1,
+                             ctx->d_meta + 2, 1, s);
+    if (rc) return rc;
+    uint32_t meta[2] = {0, 0};
+    HDLZ_CUDA(cudaMemcpyAsync(meta, ctx->d_meta + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaStreamSynchronize(s));
+    uint32_t st = meta[1];
+    if (st == HDLZ_OK && meta[0] > out_cap) st = HDLZ_ST_OUT_OVERFLOW;
+    if (st == HDLZ_OK) {
+        HDLZ_CUDA(cudaMemcpyAsync(out, ctx->d_out, meta[0], cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaStreamSynchronize(s));
+        *out_len = meta[0];
+    }
+    if (status) *status = st;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                           uint32_t *out_len, uint32_t *status, uint32_t flags)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!in || !out_len || (!out && out_cap)) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    *out_len = 0;
+    const size_t out_slot = ((size_t)out_cap + 15) & ~(size_t)15;
+    if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, (size_t)len + 16))) return rc;
+    if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_slot + 16))) return rc;
+    if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * sizeof(uint32_t)))) return rc;
+    cudaStream_t s = ctx->stream;
+    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, len, cudaMemcpyHostToDevice, s));
+    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_meta, &len, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    rc = hdlz_decompress_batch(ctx, ctx->d_in, nullptr, 0, ctx->d_meta, ctx->d_out, out_slot, out_cap, ctx->d_meta + 1,
+                               ctx->d_meta + 2, 1, flags, s);
+    if (rc) return rc;
+    uint32_t meta[2] = {0, 0};
+    HDLZ_CUDA(cudaMemcpyAsync(meta, ctx->d_meta + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaStreamSynchronize(s));
+    if (meta[1] == HDLZ_OK && meta[0]) {
+        HDLZ_CUDA(cudaMemcpyAsync(out, ctx->d_out, meta[0], cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaStreamSynchronize(s));
+    }
+    *out_len = meta[1] == HDLZ_OK ? meta[0] : 0;
+    if (status) *status = meta[1];
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_ptr) return set_error(HDLZ_ERR_INVALID, "null output pointer");
+    HDLZ_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_dev_free(hdlz_ctx *ctx, void *d_ptr)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaFree(d_ptr));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_host_alloc_pinned(hdlz_ctx *ctx, size_t bytes, void **h_ptr)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!h_ptr) return set_error(HDLZ_ERR_INVALID, "null output pointer");
+    HDLZ_CUDA(cudaMallocHost(h_ptr, bytes ? bytes : 16));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_host_free_pinned(hdlz_ctx *ctx, void *h_ptr)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaFreeHost(h_ptr));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_copy_h2d(hdlz_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_copy_d2h(hdlz_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_stream_sync(hdlz_ctx *ctx, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_generate_blocks(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,
+                         uint64_t first_block, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_out) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (len > stride) return set_error(HDLZ_ERR_INVALID, "len exceeds stride");
+    return launch_generate(ctx, d_out, stride, len, n, seed, first_block, (cudaStream_t)stream);
+}
+
+uint64_t hdlz_launch_count(hdlz_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// hdlz_common.cuh — shared declarations of libhdlz (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hdlz.h"
+
+#define HDLZ_FULL_MASK 0xFFFFFFFFu
+
+struct hdlz_ctx {
+    int device;
+    int sm_count;
+    // scratch for the host-buffer entry points (grown on demand, reused)
+    uint8_t *d_in;
+    size_t d_in_cap;
+    uint8_t *d_out;
+    size_t d_out_cap;
+    uint32_t *d_meta;  // in_len | out_len | status
+    size_t d_meta_cap;
+    uint64_t *d_off;
+    size_t d_off_cap;
+    cudaStream_t stream;  // owned, used by the host-buffer entry points
+    unsigned long long launches;
+};
+
+namespace hdlz {
+
+// error plumbing (hdlz_api.cu)
+int set_error(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define HDLZ_CUDA(call)                                   \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// kernel launchers
+int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                    uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
+                    uint32_t *d_status, uint64_t n, cudaStream_t s);
+int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
+                   const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
+                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, cudaStream_t s);
+int launch_generate(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,
+                    uint64_t first_block, cudaStream_t s);
+
+__host__ __device__ inline uint32_t compress_bound(uint32_t len)
+{
+    // 2 header + ceil((3 + 9*len + 7) / 8) + 4 Adler, rounded up to 16
+    uint64_t b = 2ull + (3ull + 9ull * len + 7ull + 7ull) / 8ull + 4ull;
+    return (uint32_t)((b + 15ull) & ~15ull);
+}
+
+}  // namespace hdlz

@@ -1,0 +1,153 @@
+/*
+ * hdlz.h — C ABI of the B200-native deflate engine (libhdlz.so).
+ *
+ * This is the drop-in boundary for the hot path of tomtor/HDL-deflate: what a
+ * host would bind by FFI (ctypes / cgo / JNI) instead of clocking the
+ * reference's `deflate()` block.  The reference has no C interface — its
+ * interface is the ten-signal port of deflate.py:220-221 driven one command
+ * per clock (deflate.py:18, 599-605, 616-654) — so each entry point below names
+ * the reference behaviour it replaces.  The Python host model that keeps the
+ * reference's port protocol on top of these calls is
+ * hdl-deflate_b200/dropin/deflate.py; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).
+ *   - functions return 0 (HDLZ_SUCCESS) or a negative hdlz_error;
+ *     hdlz_last_error() gives the text (thread-local).
+ *   - per-stream outcomes are reported in `status[]` (hdlz_status), the C
+ *     counterpart of the reference's `raise Error(...)` sites.
+ *   - *_batch functions take DEVICE pointers and are asynchronous on `stream`;
+ *     *_host / *_stream functions take HOST pointers, copy in, run the same
+ *     kernels, copy out and synchronise before returning.
+ *   - alignment: d_in, d_out 16-byte aligned; in_stride, out_stride multiples
+ *     of 16 (cudaMalloc / torch allocations satisfy this).
+ *   - the library never falls back to a CPU implementation: without a CUDA
+ *     device every compute entry point fails with HDLZ_ERR_NODEVICE.
+ */
+#ifndef HDLZ_H
+#define HDLZ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDLZ_VERSION 0x000100 /* 0.1.0 */
+
+/* Engine constants the reference exports as module globals (deflate.py:56-89). */
+#define HDLZ_CWINDOW 32      /* search window, FAST (deflate.py:56-57)               */
+#define HDLZ_MAX_MATCH 10    /* MATCH10 (deflate.py:34-35, 913-952)                  */
+#define HDLZ_MIN_INPUT 5     /* engine idles while isize < 4 (deflate.py:429-432)    */
+#define HDLZ_OBSIZE 32768    /* decompress window, "ALL valid streams" (README:20-21) */
+#define HDLZ_LMAX 24         /* width of progress / address counters (deflate.py:73-76) */
+
+typedef enum hdlz_error {
+    HDLZ_SUCCESS = 0,
+    HDLZ_ERR_INVALID = -1,  /* bad argument (null pointer, misaligned, stride too small) */
+    HDLZ_ERR_CUDA = -2,     /* a CUDA runtime call failed (text in hdlz_last_error)      */
+    HDLZ_ERR_NOMEM = -3,    /* device or pinned allocation failed                        */
+    HDLZ_ERR_NODEVICE = -4  /* no CUDA device / driver                                   */
+} hdlz_error;
+
+/* Per-stream status word.  The text in quotes is the message the reference
+ * raises at the cited line; dropin/deflate.py re-raises it as myhdl.Error.      */
+typedef enum hdlz_status {
+    HDLZ_OK = 0,
+    HDLZ_ST_SHORT_INPUT = 1,  /* compress: fewer than 5 bytes — reference never starts (deflate.py:429-432) */
+    HDLZ_ST_BAD_BTYPE = 2,    /* "Bad method" (deflate.py:718-721)                                          */
+    HDLZ_ST_BAD_CODE = 3,     /* "Invalid data" / "invalid token" / "< 1 bits" (deflate.py:1140,1439,1560)  */
+    HDLZ_ST_DIST_TOO_FAR = 4, /* "distance too big" (deflate.py:1506-1508)                                  */
+    HDLZ_ST_TRUNCATED = 5,    /* "NO EOF!" (deflate.py:1535-1539)                                           */
+    HDLZ_ST_OUT_OVERFLOW = 6, /* output does not fit out_cap / out_stride (reference: ring back-pressure, deflate.py:1531,1597) */
+    HDLZ_ST_BAD_STORED = 7,   /* stored block LEN != ~NLEN (reference does not check; zlib does)            */
+    HDLZ_ST_BAD_HEADER = 8,   /* zlib CMF/FLG invalid — only with HDLZ_F_VERIFY_HEADER (reference skips it, deflate.py:644,665-676) */
+    HDLZ_ST_BAD_ADLER = 9     /* Adler-32 mismatch — only with HDLZ_F_VERIFY_ADLER (reference never checks, deflate.py:1535)       */
+} hdlz_status;
+
+/* decompress flags */
+#define HDLZ_F_VERIFY_HEADER 1u
+#define HDLZ_F_VERIFY_ADLER 2u
+
+typedef struct hdlz_ctx hdlz_ctx;
+
+/* ---- library ------------------------------------------------------------ */
+int hdlz_version(void);
+const char *hdlz_last_error(void);
+const char *hdlz_status_name(uint32_t status);
+int hdlz_device_count(void);
+
+/* One context per (process, GPU).  Replaces instantiating the block,
+ * `dut = deflate(i_mode, ..., clk, reset)` (deflate.py:219-221; test_deflate.py:314):
+ * owns the scratch the reference keeps in iram/oram/leaves (deflate.py:229-230,277-280). */
+int hdlz_create(int device, hdlz_ctx **ctx);
+int hdlz_destroy(hdlz_ctx *ctx);
+
+/* Worst-case compressed size of `len` input bytes: 2 + ceil((3 + 9*len + 7)/8) + 4,
+ * rounded up to 16 (all-9-bit literals; CSTATIC framing deflate.py:746-814). */
+uint32_t hdlz_compress_bound(uint32_t len);
+
+/* ---- compress: STARTC job (deflate.py:618-633; CSTATIC/SEARCH/SEARCHF/DISTANCE/CHECKSUM :734-1016) ----
+ * Block i = d_in[i*in_stride .. +len_i), len_i = d_in_len ? d_in_len[i] : uniform_len
+ * (the reference's `isize + 1`, deflate.py:605).  Writes one zlib stream (78 9C, one
+ * fixed-Huffman block, Adler-32) to d_out[i*out_stride ..], its length to d_out_len[i]
+ * (the reference's o_oprogress at o_done) and the outcome to d_status[i] (may be NULL).
+ * Output is bit-identical to deflate.py with FAST=MATCH10=True, CWINDOW=32.
+ * out_stride must be >= hdlz_compress_bound(max len); bytes of the slot past
+ * out_len up to the next multiple of 4 are zeroed, the rest is left untouched. */
+int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                        uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
+                        uint32_t *d_status, uint64_t n_blocks, void *stream);
+
+/* ---- decompress: STARTD job (deflate.py:635-651; HEADER..COPY :656-732, :1084-1659) ----
+ * Stream i = d_in[off_i .. +d_in_len[i]) with off_i = d_in_off ? d_in_off[i] : i*in_stride;
+ * zlib-wrapped deflate (stored, fixed and dynamic blocks, 32 KiB window).  Plain bytes go to
+ * d_out[i*out_stride .. ] (at most out_cap), count to d_out_len[i], outcome to d_status[i].
+ * Output is byte-identical to zlib's inflate. */
+int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
+                          const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
+                          uint32_t *d_out_len, uint32_t *d_status, uint64_t n_streams, uint32_t flags,
+                          void *stream);
+
+/* ---- host-buffer forms (what a reference-side FFI stub calls) -------------
+ * Same arguments with HOST pointers; H2D copy, kernel, D2H copy, synchronise.
+ * These replace the WRITE... / START / READ... sequence of the port protocol
+ * (deflate.py:599-605; test_deflate.py:120-183, 200-274) for whole buffers. */
+int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
+                       uint32_t uniform_len, uint8_t *out, uint64_t out_stride, uint32_t *out_len,
+                       uint32_t *status, uint64_t n_blocks);
+int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint64_t in_stride,
+                         const uint32_t *in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
+                         uint32_t *out_len, uint32_t *status, uint64_t n_streams, uint32_t flags);
+
+/* One stream of any length < 2^24 (LMAX): exactly what one STARTC / STARTD job of the
+ * port protocol does.  `status` receives the hdlz_status. */
+int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                         uint32_t *out_len, uint32_t *status);
+int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                           uint32_t *out_len, uint32_t *status, uint32_t flags);
+
+/* ---- device memory helpers (for hosts without their own CUDA allocator) --- */
+int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr);
+int hdlz_dev_free(hdlz_ctx *ctx, void *d_ptr);
+int hdlz_host_alloc_pinned(hdlz_ctx *ctx, size_t bytes, void **h_ptr);
+int hdlz_host_free_pinned(hdlz_ctx *ctx, void *h_ptr);
+int hdlz_copy_h2d(hdlz_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int hdlz_copy_d2h(hdlz_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+int hdlz_stream_sync(hdlz_ctx *ctx, void *stream);
+
+/* ---- measurement support --------------------------------------------------
+ * Synthetic "random+repeat" blocks of BASELINE config 2: block b is a
+ * pure function of (seed, first_block + b); see hdl-deflate_b200/workload.py for the
+ * bit-identical CPU definition.  Kernel launches issued by this library since
+ * hdlz_create (for the bench's gpu_launches count). */
+int hdlz_generate_blocks(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n_blocks,
+                         uint64_t seed, uint64_t first_block, void *stream);
+uint64_t hdlz_launch_count(hdlz_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDLZ_H */
