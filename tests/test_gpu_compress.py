@@ -1,0 +1,134 @@
+"""Parity of the CUDA compressor (through the C ABI) with the oracle / golden vectors."""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_input
+from hdl_deflate_b200 import workload, compress_bound
+from oracle import hdlz_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_batch(arr, lens, nthreads=8):
+    n, stride = arr.shape
+    ostride = compress_bound(stride)
+    out = np.zeros((n, ostride), dtype=np.uint8)
+    out_len, status = hdlz_oracle.batch(hdlz_oracle.KIND_PORT_COMPRESS, arr, np.arange(n, dtype=np.uint64) * stride,
+                                        lens, out, np.arange(n, dtype=np.uint64) * ostride, ostride, nthreads)
+    return out, out_len, status
+
+
+def test_golden_vectors_bit_exact(engine):
+    """Fixtures produced by executing the reference FSM (oracle/make_golden.py)."""
+    for c in load_golden("compress_golden.json"):
+        data = golden_input(c)
+        got = engine.compress(data)
+        assert len(got) == c["out_len"], c["name"]
+        assert hashlib.sha256(got).hexdigest() == c["out_sha256"], c["name"]
+
+
+def test_batch_matches_oracle(engine):
+    n = 8192
+    arr = np.frombuffer(b"".join(workload.blocks(5000, n, 2048)), dtype=np.uint8).reshape(n, 2048)
+    out, out_len, status = engine.compress_host(arr)
+    want, want_len, _ = oracle_batch(arr, np.full(n, 2048, dtype=np.uint32))
+    assert not status.any()
+    assert np.array_equal(out_len, want_len)
+    mask = np.arange(out.shape[1])[None, :] < out_len[:, None]
+    assert np.array_equal(out * mask, want[:, :out.shape[1]] * mask)
+
+
+def test_ragged_and_edge_lengths(engine):
+    """Every length 0..200 plus the block-size edges, in one batch with a length array;
+    inputs shorter than 5 bytes report SHORT_INPUT (the reference never starts, deflate.py:429-432)."""
+    lens = list(range(0, 201)) + [2040, 2045, 2046, 2047, 2048] * 4
+    n = len(lens)
+    arr = np.zeros((n, 2048), dtype=np.uint8)
+    rnd = np.random.default_rng(7)
+    for i, L in enumerate(lens):
+        kind = i % 3
+        if kind == 0:
+            arr[i, :L] = np.frombuffer(workload.block(i, max(L, 1)), dtype=np.uint8)[:L]
+        elif kind == 1:
+            arr[i, :L] = rnd.integers(97, 99, L)
+        else:
+            arr[i, :L] = rnd.integers(0, 256, L)
+        arr[i, L:] = 0xEE                                  # bytes past the length must be ignored
+    lens = np.array(lens, dtype=np.uint32)
+    out, out_len, status = engine.compress_host(arr, lens)
+    for i in range(n):
+        st, want = hdlz_oracle.compress(arr[i, :lens[i]].tobytes())
+        assert status[i] == st, (i, lens[i])
+        assert out[i, :out_len[i]].tobytes() == want, (i, lens[i])
+        if st == 0:
+            assert zlib.decompress(want) == arr[i, :lens[i]].tobytes()
+
+
+@pytest.mark.parametrize("L", [2049, 2050, 2079, 2080, 2081, 4095, 4096, 4097, 10000, 65536, 100003])
+def test_long_streams_one_fixed_block(engine, L):
+    """Streams longer than a tile are still ONE fixed block (CSTATIC, deflate.py:746-814)."""
+    for kind in range(3):
+        if kind == 0:
+            data = workload.block(L, L)
+        elif kind == 1:
+            data = bytes(L)
+        else:
+            data = (b"   Hello World! %d     " % L) * (L // 20 + 1)
+            data = data[:L]
+        got = engine.compress(data)
+        assert got == hdlz_oracle.compress(data)[1]
+        assert zlib.decompress(got) == data
+
+
+def test_worst_case_and_out_overflow(engine):
+    data = bytes(np.random.default_rng(1).integers(144, 256, 2048, dtype=np.uint8))
+    got = engine.compress(data)
+    assert len(got) == 2312 and got == hdlz_oracle.compress(data)[1]
+    arr = np.frombuffer(data, dtype=np.uint8).reshape(1, 2048)
+    out, out_len, status = engine.compress_host(arr, out_stride=2304)     # < bound: refused, nothing written
+    assert status[0] == 6 and out_len[0] == 0
+
+
+def test_full_size_properties(engine):
+    """BASELINE config 2 at full size (2^20 blocks x 2 KiB) on device memory: every stream is valid
+    zlib (round trip through the GPU inflater, byte compare on device) and a checksum of all output
+    lengths / a sampled byte compare matches the oracle."""
+    import torch
+    n, L = 1 << 20, 2048
+    ostride = compress_bound(L)
+    dev = torch.device("cuda:0")
+    d_in = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n * ostride, dtype=torch.uint8, device=dev)
+    d_len = torch.empty(n, dtype=torch.int32, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    engine.generate_blocks(d_in, L, L, n, stream=s)
+    engine.compress_batch(d_in, L, None, L, d_out, ostride, d_len, d_st, n, stream=s)
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum()) == 0
+    # device generator == CPU definition on a sample
+    idx = [0, 1, 2, 12345, 524287, n - 1]
+    h_in = d_in.view(n, L)[idx].cpu().numpy()
+    for k, i in enumerate(idx):
+        assert h_in[k].tobytes() == workload.block(i, L), i
+    # sampled byte-exactness against the oracle (stride sample of 4096 blocks)
+    sel = torch.arange(0, n, n // 4096, device=dev)
+    h_blocks = d_in.view(n, L)[sel].cpu().numpy()
+    h_out = d_out.view(n, ostride)[sel].cpu().numpy()
+    h_len = d_len[sel].cpu().numpy().astype(np.uint32)
+    want, want_len, _ = oracle_batch(h_blocks, np.full(len(sel), L, dtype=np.uint32))
+    assert np.array_equal(h_len, want_len)
+    mask = np.arange(ostride)[None, :] < h_len[:, None]
+    assert np.array_equal(h_out * mask, want * mask)
+    # encode -> decode round trip of ALL blocks on the device
+    d_back = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    d_blen = torch.empty(n, dtype=torch.int32, device=dev)
+    d_bst = torch.empty(n, dtype=torch.int32, device=dev)
+    engine.decompress_batch(d_out, None, ostride, d_len, d_back, L, L, d_blen, d_bst, n, flags=3, stream=s)
+    torch.cuda.synchronize()
+    assert int(d_bst.abs().sum()) == 0
+    assert bool((d_blen == L).all())
+    assert torch.equal(d_back, d_in)

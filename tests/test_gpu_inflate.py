@@ -1,0 +1,186 @@
+"""Parity of the CUDA inflater (through the C ABI) with zlib — the reference's own decompress
+check (test_deflate.py:194) — on fixed, dynamic, stored and multi-block streams, plus the error
+statuses that stand in for the reference's `raise Error(...)` sites."""
+import hashlib
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+import hdl_deflate_b200 as hz
+from hdl_deflate_b200 import workload
+
+pytestmark = pytest.mark.gpu
+
+
+def zl(data, level=6, strategy=0, wbits=15):
+    co = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+    return co.compress(data) + co.flush()
+
+
+def test_golden_streams(engine):
+    for c in load_golden("decompress_golden.json"):
+        out = engine.decompress(bytes.fromhex(c["stream_hex"]), flags=3)
+        assert len(out) == c["out_len"] and hashlib.sha256(out).hexdigest() == c["out_sha256"], c["name"]
+
+
+def test_reference_test_modes(engine):
+    """The six data modes of test_deflate.py:38-66 at the reference's tlen=2500, zlib level 6, wbits=LOBSIZE."""
+    rnd = random.Random(11)
+    modes = [" ".join("Hello World! 1 " for _ in range(2500)).encode(),
+             " ".join("   Hello World! %d     " % i for i in range(2500)).encode(),
+             " ".join("Hi: %d " % rnd.randrange(0x1000) for _ in range(2500)).encode(),
+             bytes(rnd.randrange(256) for _ in range(2500)),
+             "".join(str(rnd.randrange(2)) for _ in range(2500)).encode(),
+             b""]
+    for b_data in modes:
+        assert engine.decompress(zl(b_data), flags=3) == b_data
+
+
+def test_mixed_batch_matches_zlib(engine):
+    rnd = random.Random(3)
+    text = " ".join("   Hello World! %d     " % i for i in range(3000)).encode()
+    plains = []
+    for t in range(96):
+        n = rnd.choice([0, 1, 2, 3, 100, 2048, 5000, 32768, 40000])
+        kind = t % 5
+        if kind == 0:
+            d = bytes(rnd.randrange(256) for _ in range(n))
+        elif kind == 1:
+            d = bytes(rnd.choice(b"abc ") for _ in range(n))
+        elif kind == 2:
+            d = text[:n]
+        elif kind == 3:
+            d = workload.block(t, max(n, 1))[:n]
+        else:
+            d = bytes([rnd.randrange(256)]) * n
+        plains.append(d)
+    streams = []
+    for i, d in enumerate(plains):
+        lvl, strat = [(6, 0), (6, zlib.Z_FIXED), (0, 0), (9, 0), (1, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)][i % 6]
+        streams.append(zl(d, lvl, strat))
+    # packed layout with an offset array (arbitrary, unaligned offsets)
+    off = np.zeros(len(streams), dtype=np.uint64)
+    pos = 0
+    for i, s in enumerate(streams):
+        off[i] = pos
+        pos += len(s) + (i % 3)
+    buf = np.zeros(pos + 16, dtype=np.uint8)
+    for i, s in enumerate(streams):
+        buf[int(off[i]):int(off[i]) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    lens = np.array([len(s) for s in streams], dtype=np.uint32)
+    out, out_len, status = engine.decompress_host(buf, lens, 40000, in_off=off, flags=3)
+    assert not status.any(), status
+    for i, d in enumerate(plains):
+        assert out[i, :out_len[i]].tobytes() == d, i
+
+
+def test_multi_block_and_window(engine):
+    """Several deflate blocks per stream (Z_FULL_FLUSH), distances up to 32 KiB."""
+    rnd = random.Random(8)
+    base = bytes(rnd.randrange(256) for _ in range(32768))
+    data = base + bytes(rnd.choice(b"xyz") for _ in range(1000)) + base[:20000] + base[100:5000]
+    co = zlib.compressobj(9, zlib.DEFLATED, 15, 9)
+    z = co.compress(data[:30000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(data[30000:60000]) + \
+        co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[60000:]) + co.flush()
+    assert engine.decompress(z, flags=3) == data
+
+
+def test_config3_zfixed_blocks(engine):
+    """BASELINE config 3 shape: 2 KiB blocks as zlib Z_FIXED streams, packed + offsets."""
+    n = 2048
+    blocks = workload.blocks(900, n, 2048)
+    streams = [zl(b, 6, zlib.Z_FIXED) for b in blocks]
+    off = np.cumsum([0] + [len(s) for s in streams[:-1]]).astype(np.uint64)
+    buf = np.frombuffer(b"".join(streams) + bytes(16), dtype=np.uint8)
+    lens = np.array([len(s) for s in streams], dtype=np.uint32)
+    out, out_len, status = engine.decompress_host(buf, lens, 2048, in_off=off)
+    assert not status.any() and (out_len == 2048).all()
+    assert out.tobytes() == b"".join(blocks)
+
+
+def test_config4_dynamic_32k(engine):
+    """BASELINE config 4 shape: 32 KiB plain, zlib level 6 dynamic trees, OBSIZE = 32768."""
+    rnd = np.random.default_rng(4)
+    n = 64
+    plains, streams = [], []
+    for i in range(n):
+        sym = rnd.zipf(1.3, 32768) % 64 + 32
+        d = bytes(sym.astype(np.uint8))
+        d = d[:20000] + d[3000:15768]
+        plains.append(d)
+        z = zl(d, 6)
+        assert (z[2] >> 1) & 3 == 2              # BTYPE = 2
+        streams.append(z)
+    stride = (max(len(s) for s in streams) + 15) & ~15
+    buf = np.zeros((n, stride), dtype=np.uint8)
+    for i, s in enumerate(streams):
+        buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    lens = np.array([len(s) for s in streams], dtype=np.uint32)
+    out, out_len, status = engine.decompress_host(buf, lens, 32768, flags=3)
+    assert not status.any() and (out_len == 32768).all()
+    for i in range(n):
+        assert out[i].tobytes() == plains[i]
+
+
+def test_error_statuses(engine):
+    z = zl(b"hello hello hello hello hello", 6)
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(z[:-5])
+    assert e.value.status == 5                                   # "NO EOF!"
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(z[:2] + bytes([z[2] | 6]) + z[3:])
+    assert e.value.status == 2 and "Bad method" in str(e.value)  # BTYPE = 3
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(z, max_out=5)
+    assert e.value.status == 6
+    bad = bytearray(z)
+    bad[-1] ^= 1
+    assert engine.decompress(bytes(bad)) == b"hello hello hello hello hello"   # reference never checks Adler
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(bytes(bad), flags=hz.F_VERIFY_ADLER)
+    assert e.value.status == 9
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(b"\x79\x9c" + z[2:], flags=hz.F_VERIFY_HEADER)
+    assert e.value.status == 8
+    # distance beyond the start of the output: fixed block, match (len 3, dist 1) as first token
+    bits = 0b011 | (64 << 3)      # BFINAL=1 BTYPE=01, symbol 257 (code 0000001, MSB first), distance code 0, EOB
+    raw = bytes([0x78, 0x9c]) + bits.to_bytes(4, "little") + bytes(4)
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(raw)
+    assert e.value.status == 4 and "distance too big" in str(e.value)
+    # the oracle agrees on every status above
+    from oracle import hdlz_oracle
+    assert hdlz_oracle.inflate(raw, 100)[0] == 4
+    st = hdlz_oracle.inflate(zl(bytes(300), 0)[:2] + b"\x01\x05\x00\x00\x00", 100)[0]
+    with pytest.raises(hz.StreamError) as e:
+        engine.decompress(zl(bytes(300), 0)[:2] + b"\x01\x05\x00\x00\x00")
+    assert e.value.status == st == 7                             # LEN != ~NLEN
+
+
+def test_corrupted_streams_never_crash(engine):
+    """Bit flips anywhere: the status is an error or the output equals zlib's; never a fault."""
+    rnd = random.Random(21)
+    data = " ".join("Hi: %d " % rnd.randrange(0x1000) for _ in range(400)).encode()
+    z = bytearray(zl(data, 6))
+    n = 256
+    stride = (len(z) + 15) & ~15
+    buf = np.zeros((n, stride), dtype=np.uint8)
+    for i in range(n):
+        c = bytearray(z)
+        for _ in range(1 + i % 3):
+            c[rnd.randrange(2, len(c))] ^= 1 << rnd.randrange(8)
+        buf[i, :len(c)] = np.frombuffer(bytes(c), dtype=np.uint8)
+    lens = np.full(n, len(z), dtype=np.uint32)
+    out, out_len, status = engine.decompress_host(buf, lens, 2 * len(data), flags=3)
+    for i in range(n):
+        try:
+            want = zlib.decompress(buf[i, :len(z)].tobytes())
+        except zlib.error:
+            want = None
+        if status[i] == 0:
+            assert want is not None and out[i, :out_len[i]].tobytes() == want, i
+        else:
+            assert want is None or len(want) > 2 * len(data), (i, status[i])
