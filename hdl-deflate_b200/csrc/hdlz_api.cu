@@ -124,6 +124,7 @@ int hdlz_destroy(hdlz_ctx *c)
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->d_off) cudaFree(c->d_off);
+    if (c->d_work) cudaFree(c->d_work);
     delete c;
     return HDLZ_SUCCESS;
 }

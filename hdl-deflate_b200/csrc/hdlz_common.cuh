@@ -7,6 +7,9 @@
 #include "hdlz.h"
 
 #define HDLZ_FULL_MASK 0xFFFFFFFFu
+// internal routing flags of hdlz_decompress_batch (tests / profiling)
+#define HDLZ_F_FORCE_GENERAL 0x100u   /* warp-per-stream kernel only */
+#define HDLZ_F_FORCE_LANES 0x200u     /* lane-per-stream kernel first, whatever the batch size */
 
 struct hdlz_ctx {
     int device;
@@ -20,6 +23,8 @@ struct hdlz_ctx {
     size_t d_meta_cap;
     uint64_t *d_off;
     size_t d_off_cap;
+    uint32_t *d_work;  // [0] count, [4..] stream ids handed from the lane kernel to the warp kernel
+    size_t d_work_cap;
     cudaStream_t stream;  // owned, used by the host-buffer entry points
     unsigned long long launches;
 };

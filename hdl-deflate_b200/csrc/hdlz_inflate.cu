@@ -206,8 +206,13 @@ __device__ __forceinline__ int decode(Reader &r, const Huff &h)
 __global__ void __launch_bounds__(kWarps * 32)
 k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint64_t in_stride,
           const uint32_t *__restrict__ in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
-          uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, uint32_t flags)
+          uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, uint32_t flags,
+          const uint32_t *__restrict__ work_list, const uint32_t *__restrict__ work_count)
 {
+    // Work items: every stream (work_list == nullptr) or the streams the lane-per-stream kernel
+    // handed over (dynamic blocks, unaligned buffers).  Persistent: warps stride over the items.
+    const uint64_t n_items = work_list ? (uint64_t)*work_count : n_streams;
+    if (n_items == 0) return;
     __shared__ WarpSmem s_warp[kWarps];
     __shared__ FixedSmem s_fixed;
     const int warp = threadIdx.x >> 5;
@@ -227,8 +232,9 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
     }
     __syncthreads();
 
-    const uint64_t sid = (uint64_t)blockIdx.x * kWarps + warp;
-    if (sid >= n_streams) return;
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < n_items; item += (uint64_t)gridDim.x * kWarps) {
+    const uint64_t sid = work_list ? (uint64_t)work_list[item] : item;
+    __syncwarp();
 
     const uint32_t n_in = in_len[sid];
     const uint8_t *src = in + (in_off ? in_off[sid] : sid * in_stride);
@@ -253,6 +259,7 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
     if (st == HDLZ_OK) {
         r.seek(2);                                   // skip the zlib header: di = 2 (deflate.py:644)
         const int64_t limit = 8 * (int64_t)n_in;
+        const uint32_t wi_guard = (r.end + 8) / 4 + 2;   // words past the stream end: stop a runaway decode
         uint32_t final_blk = 0;
         do {
             if (r.fill < 32) r.refill();
@@ -333,7 +340,7 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
             // ---- symbol loop (NEXT / INFLATE / D_NEXT / COPY, deflate.py:1402-1659) ----
             for (;;) {
                 if (r.fill < 32) r.refill();
-                if (r.wi * 32ull > (uint64_t)(r.end + 8) * 8ull) { st = HDLZ_ST_TRUNCATED; break; }
+                if (r.wi > wi_guard) { st = HDLZ_ST_TRUNCATED; break; }
                 int sym = decode(r, hl);
                 if (sym < 0) { st = HDLZ_ST_BAD_CODE; break; }
                 if (sym < 256) {
@@ -398,19 +405,22 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
         out_len[sid] = st == HDLZ_OK ? o : 0;
         if (status) status[sid] = st;
     }
+    }  // work items
 }
 
 }  // namespace
 
-int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
-                   const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
-                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, cudaStream_t s)
+int launch_inflate_general(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
+                           const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
+                           uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags,
+                           const uint32_t *work_list, const uint32_t *work_count, cudaStream_t s)
 {
     if (n == 0) return HDLZ_SUCCESS;
-    const uint64_t blocks = (n + kWarps - 1) / kWarps;
-    if (blocks > 0x7FFFFFFFull) return set_error(HDLZ_ERR_INVALID, "too many streams for one launch");
+    uint64_t blocks = (n + kWarps - 1) / kWarps;
+    const uint64_t resident = (uint64_t)ctx->sm_count * 5;       // 38 KiB of shared memory per CTA
+    if (blocks > resident) blocks = resident;
     k_inflate<<<(unsigned)blocks, kWarps * 32, 0, s>>>(d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap,
-                                                        d_out_len, d_status, n, flags);
+                                                        d_out_len, d_status, n, flags, work_list, work_count);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;

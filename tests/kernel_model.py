@@ -19,8 +19,8 @@ is spent.  See DESIGN.md "compress kernel" for the derivation.
   phase P3 forward         : mark token starts, sum bits, scan, emit at offsets
 """
 
-TILE = 2048
-SEG = 64
+TILE = 1024
+SEG = 32
 MASK32 = 0xFFFFFFFF
 
 
@@ -54,6 +54,11 @@ def match_token(d, m):
 
 def funnelshift_r(lo, hi, s):
     return (((hi << 32) | lo) >> (s & 31)) & MASK32
+
+
+def funnelshift_l(lo, hi, s):
+    s &= 31
+    return ((((hi << 32) | lo) << s) >> 32) & MASK32
 
 
 def clz32(v):
@@ -155,44 +160,55 @@ def phase_p2(Hs, carry):
 
 
 def phase_p3(tok, entries, bitbase, words):
-    """Emit the tile's tokens into `words` (dict word-index -> u32), return new bit position."""
+    """v2: ONE forward pass per segment writes the segment's started tokens into a lane-private
+    word array (flush check every second position: fill < 32 + 2*15 < 64), then a merge pass
+    shifts each private stream to its bit offset in the tile's stream (first/last word OR-ed,
+    interior words stored).  Returns the new bit position."""
     nseg = TILE // SEG
-    seg_bits = []
+    priv, nbits = [], []
     for g in range(nseg):
         r = entries[g]
-        bits = 0
-        for j in range(SEG):
-            code, nb, ln = tok[g * SEG + j]
-            start = r == 0
-            if start:
-                bits += nb
-                r = ln - 1
-            else:
-                r -= 1
-        seg_bits.append(bits)
-    pos = bitbase
-    for g in range(nseg):
-        r = entries[g]
-        bp = pos
         acc = 0
-        fill = bp & 31
-        w = bp >> 5
+        fill = 0
+        pw = []
         for j in range(SEG):
             code, nb, ln = tok[g * SEG + j]
             if r == 0:
                 acc |= code << fill
                 fill += nb
                 r = ln - 1
-                if fill >= 32:
-                    words[w] = words.get(w, 0) | (acc & MASK32)      # atomicOr
-                    w += 1
-                    acc >>= 32
-                    fill -= 32
             else:
                 r -= 1
+            if (j & 1) and fill >= 32:
+                pw.append(acc & MASK32)
+                acc >>= 32
+                fill -= 32
+        total = 32 * len(pw) + fill
         if fill:
-            words[w] = words.get(w, 0) | (acc & MASK32)
-        pos += seg_bits[g]
+            pw.append(acc & MASK32)          # fill < 32 here
+        assert fill < 32
+        priv.append(pw)
+        nbits.append(total)
+    pos = bitbase
+    for g in range(nseg):
+        sh = pos & 31
+        w0 = pos >> 5
+        nb = nbits[g]
+        if nb:
+            nwords_out = (sh + nb + 31) >> 5           # words of the final stream this lane touches
+            prev = 0
+            for i in range(nwords_out):
+                cur = priv[g][i] if i < len(priv[g]) else 0
+                val = funnelshift_l(prev, cur, sh)    # (cur << sh) | (prev >> (32 - sh))
+                prev = cur
+                first = i == 0 and sh != 0
+                last = i == nwords_out - 1 and ((sh + nb) & 31) != 0
+                if first or last:
+                    words[w0 + i] = words.get(w0 + i, 0) | val       # atomicOr
+                else:
+                    assert words.get(w0 + i, 0) == 0
+                    words[w0 + i] = val                               # plain store
+        pos += nb
     return pos
 
 

@@ -88,17 +88,59 @@ def test_multi_block_and_window(engine):
     assert engine.decompress(z, flags=3) == data
 
 
-def test_config3_zfixed_blocks(engine):
-    """BASELINE config 3 shape: 2 KiB blocks as zlib Z_FIXED streams, packed + offsets."""
+FORCE_GENERAL, FORCE_LANES = 0x100, 0x200       # internal routing flags (csrc/hdlz_common.cuh)
+
+
+@pytest.mark.parametrize("route", [0, FORCE_GENERAL, FORCE_LANES])
+def test_config3_zfixed_blocks(engine, route):
+    """BASELINE config 3 shape: 2 KiB blocks as zlib Z_FIXED streams, packed + offsets (unaligned) and
+    4-byte aligned offsets; through the lane-per-stream kernel, the warp-per-stream kernel, and the default."""
     n = 2048
     blocks = workload.blocks(900, n, 2048)
     streams = [zl(b, 6, zlib.Z_FIXED) for b in blocks]
-    off = np.cumsum([0] + [len(s) for s in streams[:-1]]).astype(np.uint64)
-    buf = np.frombuffer(b"".join(streams) + bytes(16), dtype=np.uint8)
     lens = np.array([len(s) for s in streams], dtype=np.uint32)
-    out, out_len, status = engine.decompress_host(buf, lens, 2048, in_off=off)
-    assert not status.any() and (out_len == 2048).all()
-    assert out.tobytes() == b"".join(blocks)
+    for align in (1, 4):
+        padded = [s + bytes((-len(s)) % align) for s in streams]
+        off = np.cumsum([0] + [len(s) for s in padded[:-1]]).astype(np.uint64)
+        buf = np.frombuffer(b"".join(padded) + bytes(16), dtype=np.uint8)
+        out, out_len, status = engine.decompress_host(buf, lens, 2048, in_off=off, flags=3 | route)
+        assert not status.any() and (out_len == 2048).all()
+        assert out.tobytes() == b"".join(blocks)
+
+
+@pytest.mark.parametrize("route", [FORCE_GENERAL, FORCE_LANES])
+def test_routes_agree_on_mixed_and_corrupt_streams(engine, route):
+    """Fixed, stored, dynamic (handed over by the lane kernel), long-distance and corrupted streams:
+    both routes must give zlib's bytes or an error status, never differ on valid streams."""
+    rnd = random.Random(77 + route)
+    text = " ".join("   Hello World! %d     " % i for i in range(400)).encode()
+    plains, streams = [], []
+    for t in range(1200):
+        n = rnd.choice([0, 1, 5, 64, 700, 2048, 6000])
+        kind = t % 4
+        d = [bytes(rnd.randrange(256) for _ in range(n)), text[:n], workload.block(t, max(n, 1))[:n],
+             bytes(rnd.choice(b"ab") for _ in range(n))][kind]
+        lvl, strat = [(6, zlib.Z_FIXED), (0, 0), (6, 0), (1, zlib.Z_FIXED), (9, zlib.Z_FIXED)][t % 5]
+        z = bytearray(zl(d, lvl, strat))
+        if t % 7 == 0 and len(z) > 8:
+            z[rnd.randrange(2, len(z))] ^= 1 << rnd.randrange(8)
+        plains.append(d)
+        streams.append(bytes(z))
+    stride = (max(len(s) for s in streams) + 15) & ~15
+    buf = np.zeros((len(streams), stride), dtype=np.uint8)
+    for i, s in enumerate(streams):
+        buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    lens = np.array([len(s) for s in streams], dtype=np.uint32)
+    out, out_len, status = engine.decompress_host(buf, lens, 6000, flags=3 | route)
+    for i, s in enumerate(streams):
+        try:
+            want = zlib.decompress(s)
+        except zlib.error:
+            want = None
+        if status[i] == 0:
+            assert want is not None and out[i, :out_len[i]].tobytes() == want, i
+        else:
+            assert want is None or len(want) > 6000, (i, status[i])
 
 
 def test_config4_dynamic_32k(engine):
