@@ -7,10 +7,14 @@
 //   - one THREAD per stream, 128 streams per CTA: symbol decode is inherently serial per stream,
 //     so the parallelism of a 2^20-stream batch is across streams, not inside one;
 //   - the two fixed-tree LUTs live once per CTA in shared memory;
-//   - every produced byte is packed into 32-bit words: a word goes to HBM with one store when it
-//     completes, and into a 16-word per-lane ring in shared memory (word-interleaved by lane =>
-//     bank == lane, conflict-free) that serves back-references up to 60 bytes — every match of the
-//     reference format (CWINDOW = 32).  Longer distances read the words back from global memory.
+//   - the warp runs in lock step, one symbol per lane per trip; literals and matches share ONE
+//     converged "append up to 4 bytes" step, only the match decode and copies longer than 4 bytes
+//     diverge;
+//   - produced bytes are packed into 32-bit words held in a 16-word per-lane ring in shared memory
+//     (word-interleaved by lane => bank == lane, conflict-free) that serves back-references up to
+//     120 bytes — every match of the reference format (CWINDOW = 32) — and is flushed to HBM 32 bytes
+//     at a time (two 128-bit stores = whole sectors).  Longer distances read the flushed words back
+//     from global memory.
 //   - a stream that turns out to need the general decoder (dynamic block, unaligned buffers) is
 //     appended to a device work list that the warp-per-stream kernel (hdlz_inflate.cu) consumes.
 //
@@ -28,7 +32,7 @@ int launch_inflate_general(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d
 namespace {
 
 constexpr int kLWarps = 4;
-constexpr int kRing = 16;   // words per lane
+constexpr int kRing = 32;   // words per lane (31 usable: the slot after the partial word is scratch)
 
 __constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35,
                                       43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -95,14 +99,14 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
     uint32_t st = HDLZ_OK;
     bool hand_over = false;
-    uint32_t o = 0, cw = 0;
+    uint32_t o = 0, cw = 0, flushed = 0;
     uint32_t ad_a = 1, ad_b = 0, ad_n = 0;
     const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) != 0;
     uint32_t state = S_HEADER;
 
     if (!valid) {
         state = S_DONE;
-    } else if ((reinterpret_cast<uintptr_t>(src) & 3u) || (reinterpret_cast<uintptr_t>(dst) & 3u)) {
+    } else if ((reinterpret_cast<uintptr_t>(src) & 3u) || (reinterpret_cast<uintptr_t>(dst) & 15u)) {
         hand_over = true;                              // the warp-per-stream kernel takes any alignment
         state = S_DONE;
     } else if (n_in < 2) {
@@ -135,102 +139,134 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         ++wi;
         fill += 32;
     };
-    auto adler_byte = [&](uint32_t b) {
-        ad_a += b;
-        ad_b += ad_a;
-        if (++ad_n == 5552) { ad_a %= 65521u; ad_b %= 65521u; ad_n = 0; }
-    };
-    auto emit = [&](uint32_t b) {
-        cw |= b << ((o & 3u) * 8u);
-        ++o;
-        if ((o & 3u) == 0) {
-            const uint32_t wq = (o >> 2) - 1;
-            ring[(wq & (kRing - 1)) * 32] = cw;
-            dst32[wq] = cw;
-            cw = 0;
+    auto adler_bytes = [&](uint32_t v, uint32_t m) {
+        for (uint32_t k = 0; k < m; ++k) {
+            ad_a += (v >> (8u * k)) & 255u;
+            ad_b += ad_a;
+            if (++ad_n == 5552) { ad_a %= 65521u; ad_b %= 65521u; ad_n = 0; }
         }
-        if (want_adler) adler_byte(b);
     };
-    // completed output word x (x < o >> 2): from the ring while it is recent, else back from global memory
+    // Output word x: the ring always holds the last kRing words INCLUDING the partial word being
+    // filled, so recent data needs no special case; older words come back from global memory
+    // (they were flushed: a 32-byte group is stored as soon as its last word completes).
     auto fetch = [&](uint32_t x, uint32_t wo) -> uint32_t {
-        if (x == wo) return cw;
-        if (wo - x <= (uint32_t)kRing) return ring[(x & (kRing - 1)) * 32];
+        if (wo - x < (uint32_t)(kRing - 1)) return ring[(x & (kRing - 1)) * 32];
         return dst32[x];
     };
+    // Store 32 completed bytes (two 128-bit stores = whole sectors) if this lane has them.
+    // Called at converged points of the loop; `flushed` counts the words already in global memory.
+    auto flush8 = [&]() {
+        while ((o >> 2) - flushed >= 8u) {
+            uint32_t q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = ring[((flushed + k) & (kRing - 1)) * 32];
+            uint4 *g = reinterpret_cast<uint4 *>(dst32 + flushed);
+            g[0] = make_uint4(q[0], q[1], q[2], q[3]);
+            g[1] = make_uint4(q[4], q[5], q[6], q[7]);
+            flushed += 8u;
+        }
+    };
+    // append the low m (1..4) bytes of v to the output; branch-free: the word being filled and
+    // the (possibly empty) next one are both written back to the ring
+    auto append = [&](uint32_t v, uint32_t m) {
+        v &= 0xFFFFFFFFu >> (32u - 8u * m);
+        if (want_adler) adler_bytes(v, m);
+        const uint32_t ob = o & 3u, wo = o >> 2;
+        const uint64_t comb = (uint64_t)cw | ((uint64_t)v << (8u * ob));
+        o += m;
+        ring[(wo & (kRing - 1)) * 32] = (uint32_t)comb;
+        ring[((wo + 1u) & (kRing - 1)) * 32] = (uint32_t)(comb >> 32);
+        cw = ob + m >= 4u ? (uint32_t)(comb >> 32) : (uint32_t)comb;
+    };
+    // bytes s .. s+3 of the output for a back-reference of distance `dist` (s = o - dist)
+    auto source = [&](uint32_t dist) -> uint32_t {
+        const uint32_t s = o - dist;
+        const uint32_t ws = s >> 2, wo = o >> 2;
+        const uint32_t w0 = fetch(ws, wo);
+        const uint32_t w1 = ws < wo ? fetch(ws + 1, wo) : 0u;
+        uint32_t v = __funnelshift_r(w0, w1, 8u * (s & 3u));
+        // distance < 4: the source overlaps what is being written -> period-`dist` pattern
+        const uint32_t p1 = (v & 0xFFu) * 0x01010101u, p2 = (v & 0xFFFFu) * 0x00010001u,
+                       p3 = (v & 0xFFFFFFu) | (v << 24);
+        v = dist >= 4u ? v : dist == 3u ? p3 : dist == 2u ? p2 : p1;
+        return v;
+    };
 
-    if (state != S_DONE) acc = (uint64_t)(load_word(0) >> 16);          // skip the zlib header: di = 2 (deflate.py:644)
+    if (state != S_DONE) {
+        acc = (uint64_t)(load_word(0) >> 16);          // skip the zlib header: di = 2 (deflate.py:644)
+        ring[0] = 0;
+    }
+
+    uint32_t rem = 0, dist = 1;      // bytes still to copy of the current match, its distance
+    uint32_t trip = 0;
 
     while (__any_sync(HDLZ_FULL_MASK, state != S_DONE)) {
+        // every 8 trips (a trip appends at most 4 bytes, so at most 8 words accumulate) all lanes
+        // store their completed 32-byte groups together
+        if ((++trip & 7u) == 0) flush8();
         if (state == S_FIXED) {
-            // ---- one symbol of a fixed block: NEXT / INFLATE / COPY ----
+            // ---- fixed block (NEXT / INFLATE / COPY): every trip appends at most four bytes ----
+            // A lane either continues the copy it is in (rem != 0) or decodes: up to four
+            // consecutive literals (packed into one append), or one match / end-of-block code.
             if (fill < 32) {
                 if (wi > nfull + 2) { st = HDLZ_ST_TRUNCATED; state = S_DONE; }
                 else refill();
             }
-            if (state == S_FIXED) {
-                const uint32_t e = s_lit[(uint32_t)acc & 511u];
-                const uint32_t nb = e & 15u;
-                acc >>= nb; fill -= nb;
-                const uint32_t kind = (e >> 8) & 3u;
-                if (kind == 0) {
-                    if (o >= out_cap) { st = HDLZ_ST_OUT_OVERFLOW; state = S_DONE; }
-                    else emit(e >> 16);
-                } else if (kind == 2) {
-                    const uint32_t eb = (e >> 4) & 15u;
-                    const uint32_t len = (e >> 16) + ((uint32_t)acc & ((1u << eb) - 1u));
-                    acc >>= eb; fill -= eb;
-                    if (fill < 32) refill();
-                    const uint32_t de = s_dist[(uint32_t)acc & 31u];
-                    acc >>= 5; fill -= 5;
-                    const uint32_t deb = de & 15u;
-                    const uint32_t dist = (de >> 8) + ((uint32_t)acc & ((1u << deb) - 1u));
+            const bool decode = state == S_FIXED && rem == 0;
+            const uint32_t room = out_cap - o;                       // o <= out_cap always
+            // literal run: symbol j is taken while everything before it was a literal, its code
+            // fits in the 32 valid bits, and the output has room
+            uint32_t used = 0, lits = 0, nlit = 0;
+            const uint32_t e0 = s_lit[(uint32_t)acc & 511u];
+            {
+                bool go = decode;
+                uint32_t e = e0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k) e = s_lit[(uint32_t)(acc >> used) & 511u];
+                    const uint32_t nb = e & 15u;
+                    go = go && (e & 0x300u) == 0 && used + nb <= 32u && nlit < room;
+                    lits |= go ? (e >> 16) << (8 * k) : 0u;
+                    used += go ? nb : 0u;
+                    nlit += go ? 1u : 0u;
+                }
+            }
+            if (decode && nlit == 0) {
+                // first symbol is not a literal (or no room): <length code><extra><5-bit distance code><extra>,
+                // at most 8 + 5 + 5 + 13 = 31 bits, all inside the low word of the bit buffer
+                const uint32_t a32 = (uint32_t)acc;
+                const uint32_t nb = e0 & 15u, eb = (e0 >> 4) & 15u, kind = (e0 >> 8) & 3u, base = e0 >> 16;
+                const uint32_t x1 = a32 >> nb;
+                const uint32_t len = base + (x1 & ((1u << eb) - 1u));
+                const uint32_t x2 = x1 >> eb;
+                const uint32_t de = s_dist[x2 & 31u];
+                const uint32_t deb = de & 15u;
+                const uint32_t dnew = (de >> 8) + ((x2 >> 5) & ((1u << deb) - 1u));
+                if (kind == 2u) {
+                    used = nb + eb + 5u + deb;
                     if (deb == 15u) { st = HDLZ_ST_BAD_CODE; state = S_DONE; }
-                    else {
-                        acc >>= deb; fill -= deb;
-                        if (dist > o) { st = HDLZ_ST_DIST_TOO_FAR; state = S_DONE; }       // "distance too big" (deflate.py:1506-1508)
-                        else if ((uint64_t)o + len > out_cap) { st = HDLZ_ST_OUT_OVERFLOW; state = S_DONE; }
-                        else {
-                            // LZ copy, four bytes per step (COPY, deflate.py:1627-1656, without its
-                            // one-byte-per-clock pipeline and off1/off2 special cases)
-                            uint32_t rem = len;
-                            while (rem) {
-                                const uint32_t s = o - dist;
-                                const uint32_t ws = s >> 2, wo = o >> 2;
-                                const uint32_t w0 = fetch(ws, wo);
-                                const uint32_t w1 = ws < wo ? fetch(ws + 1, wo) : 0u;
-                                uint32_t v = __funnelshift_r(w0, w1, 8u * (s & 3u));       // bytes s .. s+3
-                                if (dist < 4) {
-                                    // the source overlaps what is being written: period-`dist` pattern
-                                    v = dist == 1 ? (v & 0xFFu) * 0x01010101u
-                                        : dist == 2 ? (v & 0xFFFFu) * 0x00010001u
-                                                    : (v & 0xFFFFFFu) | (v << 24);
-                                }
-                                const uint32_t m = rem < 4u ? rem : 4u;
-                                if (m < 4u) v &= (1u << (8u * m)) - 1u;
-                                const uint32_t ob = o & 3u;
-                                const uint64_t comb = (uint64_t)cw | ((uint64_t)v << (8u * ob));
-                                if (want_adler)
-                                    for (uint32_t k = 0; k < m; ++k) adler_byte((v >> (8u * k)) & 255u);
-                                o += m;
-                                rem -= m;
-                                if (ob + m >= 4u) {
-                                    ring[(wo & (kRing - 1)) * 32] = (uint32_t)comb;
-                                    dst32[wo] = (uint32_t)comb;
-                                    cw = (uint32_t)(comb >> 32);
-                                } else {
-                                    cw = (uint32_t)comb;
-                                }
-                            }
-                        }
-                    }
-                } else if (kind == 1) {
+                    else if (dnew > o) { st = HDLZ_ST_DIST_TOO_FAR; state = S_DONE; }     // "distance too big" (deflate.py:1506-1508)
+                    else if (len > room) { st = HDLZ_ST_OUT_OVERFLOW; state = S_DONE; }
+                    else { rem = len; dist = dnew; }
+                } else if (kind == 1u) {
+                    used = nb;
                     state = final_blk ? S_DONE : S_HEADER;          // end of block
                     if (final_blk) final_blk = 2;                   // 2 = finished cleanly
+                } else if (kind == 0u) {
+                    st = HDLZ_ST_OUT_OVERFLOW;                      // a literal with no room left
+                    state = S_DONE;
                 } else {
                     st = HDLZ_ST_BAD_CODE;                          // "invalid token" (deflate.py:1559-1560)
                     state = S_DONE;
                 }
             }
+            acc >>= used; fill -= used;
+            // one append step: the literals, or up to four bytes of the copy (COPY, deflate.py:1627-1656)
+            const bool copying = rem != 0;
+            const uint32_t sv = source(copying ? dist : 0u);
+            const uint32_t m = copying ? (rem < 4u ? rem : 4u) : nlit;
+            rem -= copying ? m : 0u;
+            if (m && state != S_DONE) append(copying ? sv : lits, m);
         } else if (state == S_HEADER) {
             if (fill < 32) refill();
             final_blk = (uint32_t)acc & 1u;
@@ -260,10 +296,10 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 else { stored_left = len; state = S_STORED; }
             }
         } else if (state == S_STORED) {
-            // stored bytes, up to 8 per trip (COPY with method 0, deflate.py:1603-1616)
-            for (int k = 0; k < 8 && stored_left; ++k, --stored_left) {
+            // stored bytes, up to 4 per trip (COPY with method 0, deflate.py:1603-1616)
+            for (int k = 0; k < 4 && stored_left; ++k, --stored_left) {
                 if (fill < 8) refill();
-                emit((uint32_t)acc & 255u);
+                append((uint32_t)acc & 255u, 1);
                 acc >>= 8; fill -= 8;
             }
             if (stored_left == 0) {
@@ -277,6 +313,9 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         if (final_blk != 2) {
             st = HDLZ_ST_TRUNCATED;
         } else {
+            // words completed since the last 32-byte flush, then the bytes of the partial word
+            const uint32_t wo = o >> 2;
+            for (uint32_t x = flushed; x < wo; ++x) dst32[x] = ring[(x & (kRing - 1)) * 32];
             for (uint32_t k = 0; k < (o & 3u); ++k) dst[(o & ~3u) + k] = (uint8_t)(cw >> (8 * k));
             const uint64_t bp = (uint64_t)wi * 32 - fill;
             const uint64_t tp = (bp + 7) >> 3;                       // Adler-32 trailer must be present
