@@ -46,6 +46,25 @@ static int grow(void **p, size_t *cap, size_t need)
     return HDLZ_SUCCESS;
 }
 
+static int ensure_pipe(hdlz_ctx *ctx)
+{
+    for (int i = 0; i < 3; i++)
+        if (!ctx->pipe[i]) {
+            cudaError_t e = cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(pipe)");
+        }
+    return HDLZ_SUCCESS;
+}
+
+// streams per chunk of the *_host pipelines: large enough to fill the persistent grids, small
+// enough that copy-in, kernels and copy-out of neighbouring chunks overlap
+static inline uint64_t host_chunk(uint64_t n, uint64_t bytes_per_item)
+{
+    uint64_t c = (48ull << 20) / (bytes_per_item ? bytes_per_item : 1);
+    if (c < 8192) c = 8192;
+    return c < n ? c : n;
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int check_ctx(hdlz_ctx *ctx)
@@ -120,6 +139,8 @@ int hdlz_destroy(hdlz_ctx *c)
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
+    for (int i = 0; i < 3; i++)
+        if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_meta) cudaFree(c->d_meta);
@@ -158,8 +179,10 @@ int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
     if (out_cap > out_stride) return set_error(HDLZ_ERR_INVALID, "out_cap exceeds out_stride");
     if ((reinterpret_cast<uintptr_t>(d_in) & 3u))
         return set_error(HDLZ_ERR_INVALID, "d_in must be 4-byte aligned");
+    // hand-over list of the lane kernel: context-owned, so one decompress call per context at a time
+    if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, inflate_work_words(n) * sizeof(uint32_t)))) return rc;
     return launch_inflate(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n,
-                          flags, (cudaStream_t)stream);
+                          flags, ctx->d_work, (cudaStream_t)stream);
 }
 
 int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
@@ -176,16 +199,28 @@ int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, con
     if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_bytes))) return rc;
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
     uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
-    cudaStream_t s = ctx->stream;
-    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
-    if (in_len) HDLZ_CUDA(cudaMemcpyAsync(d_len, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    rc = hdlz_compress_batch(ctx, ctx->d_in, in_stride, in_len ? d_len : nullptr, uniform_len, ctx->d_out, out_stride,
-                             d_olen, d_st, n, s);
-    if (rc) return rc;
-    HDLZ_CUDA(cudaMemcpyAsync(out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-    HDLZ_CUDA(cudaMemcpyAsync(out_len, d_olen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (status) HDLZ_CUDA(cudaMemcpyAsync(status, d_st, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    HDLZ_CUDA(cudaStreamSynchronize(s));
+    if ((rc = ensure_pipe(ctx))) return rc;
+    // chunked three-stream pipeline: copy-in of chunk k+1, kernel of chunk k and copy-out of chunk k-1 overlap
+    const uint64_t chunk = host_chunk(n, in_stride + out_stride);
+    int k = 0;
+    for (uint64_t first = 0; first < n; first += chunk, ++k) {
+        const uint64_t m = n - first < chunk ? n - first : chunk;
+        cudaStream_t s = ctx->pipe[k % 3];
+        HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
+                                  cudaMemcpyHostToDevice, s));
+        if (in_len)
+            HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        rc = hdlz_compress_batch(ctx, ctx->d_in + first * in_stride, in_stride, in_len ? d_len + first : nullptr,
+                                 uniform_len, ctx->d_out + first * out_stride, out_stride, d_olen + first, d_st + first,
+                                 m, s);
+        if (rc) return rc;
+        HDLZ_CUDA(cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
+                                  cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (status)
+            HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
     return HDLZ_SUCCESS;
 }
 
@@ -197,6 +232,7 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
     if (rc) return rc;
     if (n == 0) return HDLZ_SUCCESS;
     if (!in || !in_len || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (out_cap > out_stride) return set_error(HDLZ_ERR_INVALID, "out_cap exceeds out_stride");
     size_t in_bytes;
     if (in_off) {
         in_bytes = 0;
@@ -213,17 +249,35 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
     if (in_off && (rc = grow((void **)&ctx->d_off, &ctx->d_off_cap, n * sizeof(uint64_t)))) return rc;
     uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
-    cudaStream_t s = ctx->stream;
-    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
-    HDLZ_CUDA(cudaMemcpyAsync(d_len, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    if (in_off) HDLZ_CUDA(cudaMemcpyAsync(ctx->d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    rc = hdlz_decompress_batch(ctx, ctx->d_in, in_off ? ctx->d_off : nullptr, in_stride, d_len, ctx->d_out, out_stride,
-                               out_cap, d_olen, d_st, n, flags, s);
-    if (rc) return rc;
-    HDLZ_CUDA(cudaMemcpyAsync(out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-    HDLZ_CUDA(cudaMemcpyAsync(out_len, d_olen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (status) HDLZ_CUDA(cudaMemcpyAsync(status, d_st, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    HDLZ_CUDA(cudaStreamSynchronize(s));
+    if ((rc = ensure_pipe(ctx))) return rc;
+    // fixed-stride input: chunked three-stream pipeline (as hdlz_compress_host); packed input: one chunk
+    const uint64_t chunk = in_off ? n : host_chunk(n, in_stride + out_stride);
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, (inflate_work_words(n) + 16 * nchunks + 16) * sizeof(uint32_t))))
+        return rc;
+    if (in_off) {
+        HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, ctx->pipe[0]));
+        HDLZ_CUDA(cudaMemcpyAsync(ctx->d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->pipe[0]));
+    }
+    int k = 0;
+    for (uint64_t first = 0; first < n; first += chunk, ++k) {
+        const uint64_t m = n - first < chunk ? n - first : chunk;
+        cudaStream_t s = ctx->pipe[k % 3];
+        if (!in_off)
+            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
+                                      cudaMemcpyHostToDevice, s));
+        HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off : nullptr,
+                            in_stride, d_len + first, ctx->d_out + first * out_stride, out_stride, out_cap,
+                            d_olen + first, d_st + first, m, flags, ctx->d_work + first + 16 * (uint64_t)k, s);
+        if (rc) return rc;
+        HDLZ_CUDA(cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
+                                  cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (status)
+            HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
     return HDLZ_SUCCESS;
 }
 

@@ -26,6 +26,7 @@ struct hdlz_ctx {
     uint32_t *d_work;  // [0] count, [4..] stream ids handed from the lane kernel to the warp kernel
     size_t d_work_cap;
     cudaStream_t stream;  // owned, used by the host-buffer entry points
+    cudaStream_t pipe[3];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls
     unsigned long long launches;
 };
 
@@ -47,7 +48,10 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
                     uint32_t *d_status, uint64_t n, cudaStream_t s);
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
-                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, cudaStream_t s);
+                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, uint32_t *d_work,
+                   cudaStream_t s);
+// words of device scratch launch_inflate needs for n streams (hand-over list of the lane kernel)
+inline size_t inflate_work_words(uint64_t n) { return (size_t)n + 8; }
 int launch_generate(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,
                     uint64_t first_block, cudaStream_t s);
 

@@ -188,22 +188,35 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 
             // ---------------- phase A: byte-equality masks ----------------------------------------
             uint32_t s1 = 0, s2 = 0;
-            for (int c = (t0 > 0 ? -1 : 0); c <= kChunks; ++c) {
-                const int i = 32 * c + lane;                 // tile-relative position
-                const uint32_t v = in_s[32 + i];
-                const uint32_t mcur = __match_any_sync(HDLZ_FULL_MASK, v);
-                const uint32_t mprev = T[v];
-                __syncwarp();
-                T[vprev] = 0;
-                __syncwarp();
-                T[v] = mcur;
-                __syncwarp();
-                vprev = v;
-                if (c >= 0) {
-                    Rw[i + (i >> 5)] = __funnelshift_r(mprev, mcur, lane);   // bit k <=> distance 32 - k
-                    if (c < kChunks) {
-                        s1 += v;                             // bytes past the stream end are zero
-                        s2 += v * (n_tile - (uint32_t)i);
+            {
+                // MATCH.ANY has ~100-150 cycles of latency under load (profiles/r01_ubench_*): keep the
+                // matches of the next two chunks in flight while the table steps of this one run
+                const int c0 = t0 > 0 ? -1 : 0;
+                uint32_t v1 = in_s[32 + 32 * c0 + lane];
+                uint32_t m1 = __match_any_sync(HDLZ_FULL_MASK, v1);
+                uint32_t v2 = in_s[32 + 32 * (c0 + 1) + lane];
+                uint32_t m2 = __match_any_sync(HDLZ_FULL_MASK, v2);
+                for (int c = c0; c <= kChunks; ++c) {
+                    const int i = 32 * c + lane;                 // tile-relative position
+                    const uint32_t v = v1, mcur = m1;
+                    v1 = v2; m1 = m2;
+                    if (c + 2 <= kChunks) {
+                        v2 = in_s[32 + 32 * (c + 2) + lane];
+                        m2 = __match_any_sync(HDLZ_FULL_MASK, v2);
+                    }
+                    const uint32_t mprev = T[v];
+                    __syncwarp();
+                    T[vprev] = 0;
+                    __syncwarp();
+                    T[v] = mcur;
+                    __syncwarp();
+                    vprev = v;
+                    if (c >= 0) {
+                        Rw[i + (i >> 5)] = __funnelshift_r(mprev, mcur, lane);   // bit k <=> distance 32 - k
+                        if (c < kChunks) {
+                            s1 += v;                             // bytes past the stream end are zero
+                            s2 += v * (n_tile - (uint32_t)i);
+                        }
                     }
                 }
             }
@@ -241,7 +254,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         }
                         const uint32_t n = (uint32_t)(sum >> ((31u - cl) & 31u));   // sum = n << (31 - cl)
                         const uint32_t x = ((k < 4 ? bv.x : bv.y) >> (8 * (k & 3))) & 255u;
-                        const uint32_t mt = DC[cl] + (__brev(n + 1) >> 25) + (n << 24);
+                        const uint32_t mt = (m3 ? DC[cl] : 0u) + (__brev(n + 1) >> 25) + (n << 24);
                         const uint32_t lt = LT[x];
                         const uint32_t tk = m3 ? mt : lt;
                         tokv[k] = tk;
@@ -265,16 +278,21 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             // ---------------- P2: entry skip count of every segment ----------------------------------
             uint32_t entry = 0;
             {
-                const uint32_t hlo = (uint32_t)H, hhi = (uint32_t)(H >> 32) & 0xFFu;
+                // every lane publishes its 10-nibble map, then all lanes walk the 32 segments with
+                // broadcast loads (one wavefront each) instead of two shuffles per step
+                unsigned long long *Hs = reinterpret_cast<unsigned long long *>(outw + 8);   // outw[0] holds pw
+                Hs[lane] = H;
+                __syncwarp();
                 uint32_t cur = carry;
-#pragma unroll
+#pragma unroll 8
                 for (int s = 0; s < 32; ++s) {
                     if (lane == s) entry = cur;
-                    const uint32_t lo = __shfl_sync(HDLZ_FULL_MASK, hlo, s);
-                    const uint32_t hi = __shfl_sync(HDLZ_FULL_MASK, hhi, s);
-                    cur = (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> (4 * cur)) & 15u;
+                    cur = (uint32_t)(Hs[s] >> (4 * cur)) & 15u;
                 }
                 carry = cur;
+                __syncwarp();
+                Hs[lane] = 0;                                // the stream buffer must be zero again
+                __syncwarp();
             }
 
             // ---------------- P3: this lane's tokens -> its private bitstream --------------------------

@@ -343,25 +343,18 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
-                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, cudaStream_t s)
+                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, uint32_t *d_work,
+                   cudaStream_t s)
 {
     if (n == 0) return HDLZ_SUCCESS;
     // Few streams: one warp each is the better mapping.  Many streams: one lane each first,
     // the warp-per-stream kernel then finishes whatever was handed over.
     const bool lanes_first = !(flags & HDLZ_F_FORCE_GENERAL) && (n >= 1024 || (flags & HDLZ_F_FORCE_LANES)) &&
-                             n < 0xFFFFFFFFull;
+                             n < 0xFFFFFFFFull && d_work != nullptr;
     if (!lanes_first)
         return launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
                                       d_status, n, flags, nullptr, nullptr, s);
-    const size_t need = (size_t)(n + 4) * sizeof(uint32_t);
-    if (need > ctx->d_work_cap) {
-        if (ctx->d_work) HDLZ_CUDA(cudaFree(ctx->d_work));
-        ctx->d_work = nullptr;
-        ctx->d_work_cap = 0;
-        HDLZ_CUDA(cudaMalloc((void **)&ctx->d_work, need));
-        ctx->d_work_cap = need;
-    }
-    uint32_t *count = ctx->d_work, *list = ctx->d_work + 4;
+    uint32_t *count = d_work, *list = d_work + 8;
     HDLZ_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
     const uint64_t blocks = (n + kLWarps * 32 - 1) / (kLWarps * 32);
     k_inflate_lanes<<<(unsigned)blocks, kLWarps * 32, 0, s>>>(d_in, d_in_off, in_stride, d_in_len, d_out, out_stride,
