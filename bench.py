@@ -321,6 +321,48 @@ def main():
         torch.cuda.synchronize()
         gather = {"what": "all_gather of out_len (4 B per block)", "ms": g0.elapsed_time(g1)}
 
+    # ---- e2e: the same step through the host-buffer C ABI (pinned host memory, copies timed), on
+    # every rank at the same time (the ranks share the host's PCIe / memory system), max over ranks
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_blocks, n)
+        h_in = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
+        h_in.copy_(d_in.view(n, BLOCK)[:ne])
+        h_comp = torch.empty((ne, ostride), dtype=torch.uint8, pin_memory=True)
+        h_back = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
+        h_clen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
+        h_blen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
+        h_st = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
+        lib, ctx = eng._lib, eng._ctx
+
+        def e2e_step():
+            rc = lib.hdlz_compress_host(ctx, h_in.data_ptr(), BLOCK, None, BLOCK, h_comp.data_ptr(), ostride,
+                                        h_clen.data_ptr(), h_st.data_ptr(), ne)
+            assert rc == 0, lib.hdlz_last_error()
+            rc = lib.hdlz_decompress_host(ctx, h_comp.data_ptr(), None, ostride, h_clen.data_ptr(), h_back.data_ptr(),
+                                          BLOCK, BLOCK, h_blen.data_ptr(), h_st.data_ptr(), ne, 0)
+            assert rc == 0, lib.hdlz_last_error()
+        e2e_step()
+        assert torch.equal(h_back, h_in)
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        te = (time.perf_counter() - t0) / args.e2e_steps
+        if dist:
+            tt = torch.tensor([te], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
+        h2d = ne * BLOCK + ne * ostride + 4 * ne
+        d2h = ne * ostride + ne * BLOCK + 4 * 4 * ne
+        e2e = {"value": 2 * ne * BLOCK * world / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "blocks_per_step_per_gpu": ne, "ms_per_step": te * 1e3,
+               "api": "hdlz_compress_host + hdlz_decompress_host (pinned host buffers, whole strides copied, "
+                      "chunked 3-stream pipeline)",
+               "note": "all %d ranks concurrently, max over ranks" % world}
+        del h_in, h_comp, h_back
+
     if rank != 0:
         if dist:
             dist.barrier()
@@ -360,38 +402,8 @@ def main():
     if gather:
         line["gather"] = gather
 
-    # ---- e2e: the same step through the host-buffer C ABI (pinned host memory, copies timed) ----
-    if not args.no_e2e:
-        ne = min(args.e2e_blocks, n)
-        h_in = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
-        h_in.copy_(d_in.view(n, BLOCK)[:ne])
-        h_comp = torch.empty((ne, ostride), dtype=torch.uint8, pin_memory=True)
-        h_back = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
-        h_clen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
-        h_blen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
-        h_st = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
-        lib, ctx = eng._lib, eng._ctx
-
-        def e2e_step():
-            rc = lib.hdlz_compress_host(ctx, h_in.data_ptr(), BLOCK, None, BLOCK, h_comp.data_ptr(), ostride,
-                                        h_clen.data_ptr(), h_st.data_ptr(), ne)
-            assert rc == 0, lib.hdlz_last_error()
-            rc = lib.hdlz_decompress_host(ctx, h_comp.data_ptr(), None, ostride, h_clen.data_ptr(), h_back.data_ptr(),
-                                          BLOCK, BLOCK, h_blen.data_ptr(), h_st.data_ptr(), ne, 0)
-            assert rc == 0, lib.hdlz_last_error()
-        e2e_step()
-        assert torch.equal(h_back, h_in)
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        te = (time.perf_counter() - t0) / args.e2e_steps
-        h2d = ne * BLOCK + ne * ostride + 4 * ne
-        d2h = ne * ostride + ne * BLOCK + 4 * 4 * ne
-        line["e2e"] = {"value": 2 * ne * BLOCK * world / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "blocks_per_step": ne, "ms_per_step": te * 1e3,
-                       "api": "hdlz_compress_host + hdlz_decompress_host (pinned host buffers, whole strides copied, chunked 3-stream pipeline)",
-                       "note": "per-rank figure x n_gpus" if world > 1 else "single GPU"}
-        del h_in, h_comp, h_back
+    if e2e:
+        line["e2e"] = e2e
 
     # ---- cpu_baseline: the oracle port on the host cores, bounded sample, N = 1 only ----
     if world == 1 and not args.no_cpu:
