@@ -242,6 +242,15 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
 
     uint32_t st = HDLZ_OK;
     uint32_t o = 0;
+    // Literals are parked in registers — the byte for output position p sits in lane p % 32 — and
+    // go to memory 32 at a time (one coalesced store) or right before something reads the output.
+    uint32_t of = 0;                 // positions below `of` are in memory; of <= o <= of + 32
+    uint32_t pend = 0;
+    auto flush_literals = [&]() {
+        const uint32_t p = of + (((uint32_t)lane - of) & 31u);
+        if (p < o) dst[p] = (uint8_t)pend;
+        of = o;
+    };
 
     Reader r;
     r.lane = lane;
@@ -275,8 +284,10 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
                 if ((len ^ 0xFFFFu) != nlen) { st = HDLZ_ST_BAD_STORED; break; }
                 if ((uint64_t)byte + 4 + len > n_in) { st = HDLZ_ST_TRUNCATED; break; }
                 if ((uint64_t)o + len > out_cap) { st = HDLZ_ST_OUT_OVERFLOW; break; }
+                flush_literals();
                 for (uint32_t k = lane; k < len; k += 32) dst[o + k] = src[byte + 4 + k];
                 o += len;
+                of = o;
                 r.seek(byte + 4 + len);
                 continue;
             }
@@ -339,14 +350,17 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
 
             // ---- symbol loop (NEXT / INFLATE / D_NEXT / COPY, deflate.py:1402-1659) ----
             for (;;) {
-                if (r.fill < 32) r.refill();
-                if (r.wi > wi_guard) { st = HDLZ_ST_TRUNCATED; break; }
+                if (r.fill < 32) {
+                    r.refill();
+                    if (r.wi > wi_guard) { st = HDLZ_ST_TRUNCATED; break; }
+                }
                 int sym = decode(r, hl);
                 if (sym < 0) { st = HDLZ_ST_BAD_CODE; break; }
                 if (sym < 256) {
                     if (o >= out_cap) { st = HDLZ_ST_OUT_OVERFLOW; break; }
-                    if (lane == 0) dst[o] = (uint8_t)sym;
+                    if ((uint32_t)lane == (o & 31u)) pend = (uint32_t)sym;
                     ++o;
+                    if (o - of == 32u) flush_literals();
                     continue;
                 }
                 if (sym == 256) break;
@@ -360,6 +374,7 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
                 const uint32_t dist = c_dist_base[dsym] + r.get(dbits);
                 if (dist > o) { st = HDLZ_ST_DIST_TOO_FAR; break; }        // "distance too big" (deflate.py:1506-1508)
                 if ((uint64_t)o + len > out_cap) { st = HDLZ_ST_OUT_OVERFLOW; break; }
+                flush_literals();
                 __syncwarp();
                 if (dist >= len) {
                     for (uint32_t k = lane; k < len; k += 32) dst[o + k] = dst[o - dist + k];
@@ -368,11 +383,13 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
                 }
                 __syncwarp();
                 o += len;
+                of = o;
             }
             if (st != HDLZ_OK) break;
             if (r.bitpos() > limit) { st = HDLZ_ST_TRUNCATED; break; }
         } while (!final_blk);
 
+        flush_literals();
         if (st == HDLZ_OK) {
             // Adler-32 trailer: four bytes after the next byte boundary must exist ("NO EOF!", deflate.py:1535-1539)
             const int64_t bp = r.bitpos();
