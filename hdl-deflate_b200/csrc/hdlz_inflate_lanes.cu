@@ -182,14 +182,21 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     auto source = [&](uint32_t dist) -> uint32_t {
         const uint32_t s = o - dist;
         const uint32_t ws = s >> 2, wo = o >> 2;
-        const uint32_t w0 = fetch(ws, wo);
-        const uint32_t w1 = ws < wo ? fetch(ws + 1, wo) : 0u;
-        uint32_t v = __funnelshift_r(w0, w1, 8u * (s & 3u));
-        // distance < 4: the source overlaps what is being written -> period-`dist` pattern
-        const uint32_t p1 = (v & 0xFFu) * 0x01010101u, p2 = (v & 0xFFFFu) * 0x00010001u,
-                       p3 = (v & 0xFFFFFFu) | (v << 24);
-        v = dist >= 4u ? v : dist == 3u ? p3 : dist == 2u ? p2 : p1;
-        return v;
+        uint32_t w0, w1;
+        if (wo - ws < (uint32_t)(kRing - 1)) {         // both words are in the ring (ws + 1 <= wo + 1: scratch slot)
+            w0 = ring[(ws & (kRing - 1)) * 32];
+            w1 = ring[((ws + 1u) & (kRing - 1)) * 32];
+        } else {                                       // far back-reference: flushed long ago
+            w0 = dst32[ws];
+            w1 = dst32[ws + 1u];
+        }
+        const uint32_t v = __funnelshift_r(w0, w1, 8u * (s & 3u));
+        // distance < 4: the source overlaps what is being written -> period-`dist` pattern:
+        // keep the first `dist` bytes and replicate them with one multiply
+        const uint32_t dd = dist < 4u ? dist : 4u;
+        const uint32_t keep = 0xFFFFFFFFu >> ((32u - 8u * dd) & 31u);   // dd == 0 only on lanes that are not copying
+        const uint32_t mult = dd == 4u ? 1u : dd == 3u ? 0x01000001u : dd == 2u ? 0x00010001u : 0x01010101u;
+        return (v & keep) * mult;
     };
 
     if (state != S_DONE) {
@@ -217,24 +224,25 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             // literal run: symbol j is taken while everything before it was a literal, its code
             // fits in the 32 valid bits, and the output has room
             uint32_t used = 0, lits = 0, nlit = 0;
-            const uint32_t e0 = s_lit[(uint32_t)acc & 511u];
+            const uint32_t a32 = (uint32_t)acc;                      // >= 32 valid bits
+            const uint32_t e0 = s_lit[a32 & 511u];
             {
                 bool go = decode;
-                uint32_t e = e0;
+                uint32_t e = e0, x = a32;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (k) e = s_lit[(uint32_t)(acc >> used) & 511u];
+                    if (k) e = s_lit[x & 511u];
                     const uint32_t nb = e & 15u;
                     go = go && (e & 0x300u) == 0 && used + nb <= 32u && nlit < room;
-                    lits |= go ? (e >> 16) << (8 * k) : 0u;
+                    lits |= go ? ((e >> 16) << (8 * k)) : 0u;
                     used += go ? nb : 0u;
                     nlit += go ? 1u : 0u;
+                    x >>= nb;                                        // only meaningful while go holds
                 }
             }
             if (decode && nlit == 0) {
                 // first symbol is not a literal (or no room): <length code><extra><5-bit distance code><extra>,
                 // at most 8 + 5 + 5 + 13 = 31 bits, all inside the low word of the bit buffer
-                const uint32_t a32 = (uint32_t)acc;
                 const uint32_t nb = e0 & 15u, eb = (e0 >> 4) & 15u, kind = (e0 >> 8) & 3u, base = e0 >> 16;
                 const uint32_t x1 = a32 >> nb;
                 const uint32_t len = base + (x1 & ((1u << eb) - 1u));
