@@ -328,19 +328,23 @@ def main():
         ne = min(args.e2e_blocks, n)
         h_in = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
         h_in.copy_(d_in.view(n, BLOCK)[:ne])
-        h_comp = torch.empty((ne, ostride), dtype=torch.uint8, pin_memory=True)
+        h_comp = torch.empty(ne * ostride, dtype=torch.uint8, pin_memory=True)       # packed streams land here
+        h_off = torch.zeros(ne, dtype=torch.int64, pin_memory=True)
         h_back = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
         h_clen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
         h_blen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
         h_st = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
         lib, ctx = eng._lib, eng._ctx
+        import ctypes
+        total = ctypes.c_uint64(0)
 
         def e2e_step():
-            rc = lib.hdlz_compress_host(ctx, h_in.data_ptr(), BLOCK, None, BLOCK, h_comp.data_ptr(), ostride,
-                                        h_clen.data_ptr(), h_st.data_ptr(), ne)
+            rc = lib.hdlz_compress_host_packed(ctx, h_in.data_ptr(), BLOCK, None, BLOCK, h_comp.data_ptr(),
+                                               ne * ostride, h_off.data_ptr(), h_clen.data_ptr(), h_st.data_ptr(), ne,
+                                               ctypes.byref(total))
             assert rc == 0, lib.hdlz_last_error()
-            rc = lib.hdlz_decompress_host(ctx, h_comp.data_ptr(), None, ostride, h_clen.data_ptr(), h_back.data_ptr(),
-                                          BLOCK, BLOCK, h_blen.data_ptr(), h_st.data_ptr(), ne, 0)
+            rc = lib.hdlz_decompress_host(ctx, h_comp.data_ptr(), h_off.data_ptr(), 0, h_clen.data_ptr(),
+                                          h_back.data_ptr(), BLOCK, BLOCK, h_blen.data_ptr(), h_st.data_ptr(), ne, 0)
             assert rc == 0, lib.hdlz_last_error()
         e2e_step()
         assert torch.equal(h_back, h_in)
@@ -354,11 +358,12 @@ def main():
             tt = torch.tensor([te], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             te = float(tt.item())
-        h2d = ne * BLOCK + ne * ostride + 4 * ne
-        d2h = ne * ostride + ne * BLOCK + 4 * 4 * ne
+        pk = int(total.value)
+        h2d = ne * BLOCK + pk + (8 + 4) * ne                 # blocks; packed streams + offsets + lengths
+        d2h = pk + (8 + 4 + 4) * ne + ne * BLOCK + (4 + 4) * ne
         e2e = {"value": 2 * ne * BLOCK * world / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "blocks_per_step_per_gpu": ne, "ms_per_step": te * 1e3,
-               "api": "hdlz_compress_host + hdlz_decompress_host (pinned host buffers, whole strides copied, "
+               "api": "hdlz_compress_host_packed + hdlz_decompress_host (pinned host buffers, packed streams, "
                       "chunked 3-stream pipeline)",
                "note": "all %d ranks concurrently, max over ranks" % world}
         del h_in, h_comp, h_back

@@ -152,6 +152,31 @@ class Engine(object):
                                                  _ptr(out), out_stride, _ptr(out_len), _ptr(status), n))
         return out, out_len, status
 
+    def compress_host_packed(self, blocks, lens=None):
+        """As compress_host, but the streams come back packed (starts 4-byte aligned).
+        -> (packed uint8 [total], off uint64 [n], out_len uint32 [n], status uint32 [n])."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+        n, in_stride = blocks.shape
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, dtype=np.uint32)
+            maxlen = int(lens.max()) if n else 0
+        else:
+            maxlen = in_stride
+        cap = n * compress_bound(maxlen)
+        out = np.empty(max(cap, 16), dtype=np.uint8)
+        off = np.zeros(n, dtype=np.uint64)
+        out_len = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint32)
+        total = ctypes.c_uint64(0)
+        self._check(self._lib.hdlz_compress_host_packed(self._ctx, _ptr(blocks), in_stride, _ptr(lens), in_stride,
+                                                        _ptr(out), cap, _ptr(off), _ptr(out_len), _ptr(status), n,
+                                                        ctypes.byref(total)))
+        return out[:total.value], off, out_len, status
+
+    def pack_batch(self, d_slots, stride, d_len, d_packed, d_off, d_total, n, stream=0):
+        self._check(self._lib.hdlz_pack_batch(self._ctx, _ptr(d_slots), stride, _ptr(d_len), _ptr(d_packed),
+                                              _ptr(d_off), _ptr(d_total), n, stream or None))
+
     def decompress_host(self, data, in_len, out_cap, in_off=None, in_stride=0, out_stride=None, flags=0):
         """data: uint8 buffer holding the streams (packed with in_off, or [n, in_stride]).
         -> (out uint8 [n, out_stride], out_len, status)."""

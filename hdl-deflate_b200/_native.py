@@ -24,6 +24,9 @@ SIGNATURES = {
     "hdlz_decompress_batch": (cint, [vp, c_u8p, c_u64p, u64, c_u32p, c_u8p, u64, u32, c_u32p, c_u32p, u64, u32, vp]),
     "hdlz_compress_host": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u32p, c_u32p, u64]),
     "hdlz_decompress_host": (cint, [vp, c_u8p, c_u64p, u64, c_u32p, c_u8p, u64, u32, c_u32p, c_u32p, u64, u32]),
+    "hdlz_pack_batch": (cint, [vp, c_u8p, u64, c_u32p, c_u8p, c_u64p, c_u64p, u64, vp]),
+    "hdlz_compress_host_packed": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u64p, c_u32p, c_u32p, u64,
+                                         ctypes.POINTER(u64)]),
     "hdlz_compress_stream": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "hdlz_decompress_stream": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), u32]),
     "hdlz_dev_alloc": (cint, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),

@@ -146,6 +146,8 @@ int hdlz_destroy(hdlz_ctx *c)
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_work) cudaFree(c->d_work);
+    if (c->d_pack) cudaFree(c->d_pack);
+    if (c->h_small) cudaFreeHost(c->h_small);
     delete c;
     return HDLZ_SUCCESS;
 }
@@ -250,24 +252,30 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
     if (in_off && (rc = grow((void **)&ctx->d_off, &ctx->d_off_cap, n * sizeof(uint64_t)))) return rc;
     uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
     if ((rc = ensure_pipe(ctx))) return rc;
-    // fixed-stride input: chunked three-stream pipeline (as hdlz_compress_host); packed input: one chunk
-    const uint64_t chunk = in_off ? n : host_chunk(n, in_stride + out_stride);
+    // chunked three-stream pipeline (as hdlz_compress_host).  Packed input is chunked too when its
+    // offsets ascend (what hdlz_pack_batch produces); otherwise it goes in one piece.
+    bool ascending = true;
+    if (in_off)
+        for (uint64_t i = 1; i < n && ascending; i++) ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1];
+    const uint64_t chunk = (in_off && !ascending) ? n : host_chunk(n, (in_off ? in_bytes / n + 1 : in_stride) + out_stride);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, (inflate_work_words(n) + 16 * nchunks + 16) * sizeof(uint32_t))))
         return rc;
-    if (in_off) {
-        HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, ctx->pipe[0]));
-        HDLZ_CUDA(cudaMemcpyAsync(ctx->d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->pipe[0]));
-    }
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
         cudaStream_t s = ctx->pipe[k % 3];
-        if (!in_off)
+        if (in_off) {
+            const uint64_t lo = (nchunks == 1 ? 0 : in_off[first]) & ~(uint64_t)15;
+            const uint64_t hi = nchunks == 1 ? in_bytes : in_off[first + m - 1] + in_len[first + m - 1];
+            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, s));
+            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_off + first, in_off + first, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        } else {
             HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                       cudaMemcpyHostToDevice, s));
+        }
         HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off : nullptr,
+        rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off + first : nullptr,
                             in_stride, d_len + first, ctx->d_out + first * out_stride, out_stride, out_cap,
                             d_olen + first, d_st + first, m, flags, ctx->d_work + first + 16 * (uint64_t)k, s);
         if (rc) return rc;
@@ -278,6 +286,97 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
             HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_pack_batch(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
+                    uint64_t *d_off, uint64_t *d_total, uint64_t n, void *stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (n == 0) return HDLZ_SUCCESS;
+    if (!d_slots || !d_len || !d_packed || !d_off || !d_total) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(d_slots) & 3u) || (reinterpret_cast<uintptr_t>(d_packed) & 3u) || (stride & 3u))
+        return set_error(HDLZ_ERR_INVALID, "slots, packed buffer and stride must be 4-byte aligned");
+    return launch_pack(ctx, d_slots, stride, d_len, d_packed, d_off, d_total, n, (cudaStream_t)stream);
+}
+
+int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
+                              uint32_t uniform_len, uint8_t *out, uint64_t out_cap, uint64_t *out_off,
+                              uint32_t *out_len, uint32_t *status, uint64_t n, uint64_t *out_total)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (out_total) *out_total = 0;
+    if (n == 0) return HDLZ_SUCCESS;
+    if (!in || !out || !out_off || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (in_stride & 15) return set_error(HDLZ_ERR_INVALID, "in_stride must be a multiple of 16");
+    uint32_t maxlen = uniform_len;
+    if (in_len) {
+        maxlen = 0;
+        for (uint64_t i = 0; i < n; i++) maxlen = in_len[i] > maxlen ? in_len[i] : maxlen;
+    }
+    const uint64_t slot = compress_bound(maxlen);
+    const uint64_t chunk = host_chunk(n, in_stride + slot);
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, (size_t)n * in_stride))) return rc;
+    if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, (size_t)n * slot))) return rc;
+    if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
+    if ((rc = grow((void **)&ctx->d_pack, &ctx->d_pack_cap, (size_t)n * slot + (n + nchunks + 2) * sizeof(uint64_t))))
+        return rc;
+    if (nchunks + 1 > ctx->h_small_cap) {
+        if (ctx->h_small) cudaFreeHost(ctx->h_small);
+        ctx->h_small = nullptr;
+        ctx->h_small_cap = 0;
+        HDLZ_CUDA(cudaMallocHost((void **)&ctx->h_small, (nchunks + 64) * sizeof(uint64_t)));
+        ctx->h_small_cap = nchunks + 64;
+    }
+    if ((rc = ensure_pipe(ctx))) return rc;
+    uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
+    uint8_t *d_packed = ctx->d_pack;                                               // chunk c packs into its slot range
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(ctx->d_pack + (((size_t)n * slot + 15) & ~(size_t)15));
+    uint64_t *d_tot = d_off + n;
+    uint64_t *h_tot = ctx->h_small;
+    uint64_t base = 0;
+    // stage 1 (copy in, compress, pack, small copies out) of chunk c is enqueued two chunks ahead of
+    // stage 2 (packed bytes out), which needs the chunk's packed size on the host
+    for (uint64_t c = 0; c < nchunks + 2; ++c) {
+        if (c < nchunks) {
+            const uint64_t first = c * chunk, m = n - first < chunk ? n - first : chunk;
+            cudaStream_t s = ctx->pipe[c % 3];
+            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
+                                      cudaMemcpyHostToDevice, s));
+            if (in_len)
+                HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            rc = hdlz_compress_batch(ctx, ctx->d_in + first * in_stride, in_stride, in_len ? d_len + first : nullptr,
+                                     uniform_len, ctx->d_out + first * slot, slot, d_olen + first, d_st + first, m, s);
+            if (rc) return rc;
+            rc = launch_pack(ctx, ctx->d_out + first * slot, slot, d_olen + first, d_packed + first * slot, d_off + first,
+                             d_tot + c, m, s);
+            if (rc) return rc;
+            HDLZ_CUDA(cudaMemcpyAsync(h_tot + c, d_tot + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA(cudaMemcpyAsync(out_off + first, d_off + first, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA(cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (status)
+                HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        }
+        if (c >= 2) {
+            const uint64_t cc = c - 2, first = cc * chunk, m = n - first < chunk ? n - first : chunk;
+            cudaStream_t s = ctx->pipe[cc % 3];
+            HDLZ_CUDA(cudaStreamSynchronize(s));
+            const uint64_t tot = h_tot[cc];
+            if (base + tot > out_cap) {
+                for (int i = 0; i < 3; i++) cudaStreamSynchronize(ctx->pipe[i]);
+                return set_error(HDLZ_ERR_INVALID, "packed output needs more than out_cap = %llu bytes",
+                                 (unsigned long long)out_cap);
+            }
+            HDLZ_CUDA(cudaMemcpyAsync(out + base, d_packed + first * slot, tot, cudaMemcpyDeviceToHost, s));
+            for (uint64_t i = first; i < first + m; i++) out_off[i] += base;      // chunk-local -> global offsets
+            base += tot;
+        }
+    }
+    for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
+    if (out_total) *out_total = base;
     return HDLZ_SUCCESS;
 }
 

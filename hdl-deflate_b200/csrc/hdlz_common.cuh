@@ -23,6 +23,10 @@ struct hdlz_ctx {
     size_t d_meta_cap;
     uint64_t *d_off;
     size_t d_off_cap;
+    uint8_t *d_pack;   // packed streams + per-chunk offsets/totals of hdlz_compress_host_packed
+    size_t d_pack_cap;
+    uint64_t *h_small;  // pinned: per-chunk packed sizes
+    size_t h_small_cap;
     uint32_t *d_work;  // [0] count, [4..] stream ids handed from the lane kernel to the warp kernel
     size_t d_work_cap;
     cudaStream_t stream;  // owned, used by the host-buffer entry points
@@ -52,6 +56,8 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
                    cudaStream_t s);
 // words of device scratch launch_inflate needs for n streams (hand-over list of the lane kernel)
 inline size_t inflate_work_words(uint64_t n) { return (size_t)n + 8; }
+int launch_pack(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
+                uint64_t *d_off, uint64_t *d_total, uint64_t n, cudaStream_t s);
 int launch_generate(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,
                     uint64_t first_block, cudaStream_t s);
 

@@ -122,6 +122,20 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
                          const uint32_t *in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
                          uint32_t *out_len, uint32_t *status, uint64_t n_streams, uint32_t flags);
 
+/* ---- packed stream layout -------------------------------------------------
+ * hdlz_pack_batch: device, asynchronous.  Packs the fixed-stride slots of a compress batch
+ * contiguously: stream i goes to d_packed[d_off[i] .. +d_len[i]) with d_off[i] the exclusive prefix
+ * sum of the lengths rounded up to 4; *d_total (device) receives the packed size.  d_off feeds
+ * hdlz_decompress_batch directly.  d_packed needs sum(round4(len)) bytes (<= n * stride).
+ * hdlz_compress_host_packed: hdlz_compress_host, but `out` (capacity out_cap bytes) receives the
+ * streams packed and out_off[i] their offsets; *out_total the bytes used.  Only real stream bytes
+ * are copied back.  The reference has no counterpart (its oram holds one stream, deflate.py:230). */
+int hdlz_pack_batch(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len,
+                    uint8_t *d_packed, uint64_t *d_off, uint64_t *d_total, uint64_t n_streams, void *stream);
+int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
+                              uint32_t uniform_len, uint8_t *out, uint64_t out_cap, uint64_t *out_off,
+                              uint32_t *out_len, uint32_t *status, uint64_t n_blocks, uint64_t *out_total);
+
 /* One stream of any length < 2^24 (LMAX): exactly what one STARTC / STARTD job of the
  * port protocol does.  `status` receives the hdlz_status. */
 int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,

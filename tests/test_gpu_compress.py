@@ -92,6 +92,33 @@ def test_worst_case_and_out_overflow(engine):
     assert status[0] == 6 and out_len[0] == 0
 
 
+def test_packed_host_round_trip(engine):
+    """hdlz_compress_host_packed (several pipeline chunks) -> every stream equals the oracle's, offsets are
+    the 4-byte-rounded prefix sum; hdlz_decompress_host on the packed layout gives the blocks back."""
+    n = 30011
+    arr = np.frombuffer(b"".join(workload.blocks(70000, n, 2048)), dtype=np.uint8).reshape(n, 2048)
+    packed, off, out_len, status = engine.compress_host_packed(arr)
+    assert not status.any()
+    want, want_len, _ = oracle_batch(arr, np.full(n, 2048, dtype=np.uint32))
+    assert np.array_equal(out_len, want_len)
+    exp_off = np.concatenate([[0], np.cumsum((want_len.astype(np.int64) + 3) & ~3)[:-1]]).astype(np.uint64)
+    assert np.array_equal(off, exp_off)
+    assert len(packed) == int(exp_off[-1]) + ((int(want_len[-1]) + 3) & ~3)
+    for i in list(range(0, n, 997)) + [n - 1]:
+        assert packed[int(off[i]):int(off[i]) + int(out_len[i])].tobytes() == want[i, :want_len[i]].tobytes(), i
+    back, back_len, bst = engine.decompress_host(packed, out_len, 2048, in_off=off, flags=3)
+    assert not bst.any() and (back_len == 2048).all()
+    assert np.array_equal(back, arr)
+    # ragged lengths through the packed path
+    lens = np.array([(5 + 37 * i) % 2049 for i in range(2000)], dtype=np.uint32)
+    lens[lens < 5] = 5
+    small = arr[:2000].copy()
+    packed, off, out_len, status = engine.compress_host_packed(small, lens)
+    for i in range(0, 2000, 61):
+        assert packed[int(off[i]):int(off[i]) + int(out_len[i])].tobytes() == \
+            hdlz_oracle.compress(small[i, :lens[i]].tobytes())[1], i
+
+
 def test_full_size_properties(engine):
     """BASELINE config 2 at full size (2^20 blocks x 2 KiB) on device memory: every stream is valid
     zlib (round trip through the GPU inflater, byte compare on device) and a checksum of all output
