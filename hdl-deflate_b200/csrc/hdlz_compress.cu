@@ -46,21 +46,24 @@ constexpr int kTile = 1024;            // positions per tile
 constexpr int kSeg = 32;               // positions per lane in the segment phases
 constexpr int kChunks = kTile / 32;
 constexpr int kWarpsPerCta = 4;
-constexpr int kCtasPerSm = 7;
+constexpr int kCtasPerSm = 8;
 constexpr int kInBytes = 32 + kTile + 32;              // history | tile | look-ahead chunk
-constexpr int kPrivWords = kSeg * 9 / 32;              // 9 words: 32 positions x 9 bits
-constexpr int kStageBytes = kPrivWords * 32 * 4;       // 1152 >= kInBytes: input tile, later the private streams
+// a lane's private stream holds the tokens that START in its segment: at most 31 nine-bit literals
+// plus one 15-bit match token at the last position = 294 bits
+constexpr int kPrivWords = ((kSeg - 1) * 9 + 15 + 31) / 32;   // 10
+constexpr int kStageBytes = kPrivWords * 32 * 4;       // 1280 >= kInBytes: input tile, later the private streams
 constexpr int kRWords = (kTile + 32) + (kTile + 32) / kSeg;   // padded: idx = i + i/32  (1089 incl. last +1)
 constexpr int kOutWords = 296;                         // 31 carry bits + 1024*9 + EOB + Adler, rounded up
 
 static_assert(kStageBytes >= kInBytes, "stage buffer must hold the input tile");
 
 struct __align__(16) WarpSmem {
-    uint8_t stage[kStageBytes];                        // input tile, later the lane-private streams
-    uint32_t R[(kRWords + 4) / 4 * 4];                 // masks, overwritten in place by tokens
+    uint8_t stage[kStageBytes];                        // input tile, then the segment maps, then the lane-private streams
+    uint32_t R[(kRWords + 4) / 4 * 4];                 // masks, overwritten in place by tokens; after P3 the
+                                                       // tile's part of the output stream (kOutWords words)
     uint32_t T[256];                                   // value -> lane mask of the previous chunk
-    uint32_t outw[kOutWords];                          // the tile's part of the stream
 };
+static_assert(kOutWords <= kRWords, "the output stream part must fit in the token array");
 
 constexpr int kLutWords = 256 + 36;   // LT[256] literal tokens, DC[33] distance part of match tokens
 constexpr size_t kSmemBytes = kLutWords * 4 + sizeof(WarpSmem) * kWarpsPerCta;
@@ -132,7 +135,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
     uint32_t *priv = reinterpret_cast<uint32_t *>(ws.stage);   // word k of lane l at priv[k * 32 + l]
     uint32_t *Rw = ws.R;
     uint32_t *T = ws.T;
-    uint32_t *outw = ws.outw;
+    uint32_t *outw = ws.R;                                      // valid only after P3 (tokens are dead then)
 
     for (int i = lane; i < 256; i += 32) T[i] = 0;
     uint32_t vprev = 0;
@@ -179,12 +182,9 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     reinterpret_cast<uint4 *>(in_s)[k] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            // the stream part of the tile's output buffer starts as zeros + the carried partial word
-            for (int k = lane; k < kOutWords / 4; k += 32) reinterpret_cast<uint4 *>(outw)[k] = make_uint4(0, 0, 0, 0);
             T[vprev] = 0;                // drop the last chunk seen (previous tile's look-ahead / previous stream)
             asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             __syncwarp();
-            if (lane == 0) outw[0] = pw;
 
             // ---------------- phase A: byte-equality masks ----------------------------------------
             uint32_t s1 = 0, s2 = 0;
@@ -280,7 +280,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             {
                 // every lane publishes its 10-nibble map, then all lanes walk the 32 segments with
                 // broadcast loads (one wavefront each) instead of two shuffles per step
-                unsigned long long *Hs = reinterpret_cast<unsigned long long *>(outw + 8);   // outw[0] holds pw
+                unsigned long long *Hs = reinterpret_cast<unsigned long long *>(ws.stage);    // input bytes are dead
                 Hs[lane] = H;
                 __syncwarp();
                 uint32_t cur = carry;
@@ -290,8 +290,6 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     cur = (uint32_t)(Hs[s] >> (4 * cur)) & 15u;
                 }
                 carry = cur;
-                __syncwarp();
-                Hs[lane] = 0;                                // the stream buffer must be zero again
                 __syncwarp();
             }
 
@@ -319,7 +317,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         fill -= 32;
                     }
                 }
-                if (fill) priv[wcnt * 32 + lane] = (uint32_t)acc;
+                if (fill) priv[wcnt * 32 + lane] = (uint32_t)acc;     // wcnt <= kPrivWords - 1 here
                 nbits = 32 * wcnt + fill;
             }
             uint32_t incl = nbits;
@@ -329,6 +327,13 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 if (lane >= d) incl += o;
             }
             const uint32_t tile_bits = __shfl_sync(HDLZ_FULL_MASK, incl, 31);
+
+            // the tokens are dead: their array becomes the tile's part of the output stream
+            __syncwarp();
+            for (int k = lane; k < kOutWords / 4; k += 32) reinterpret_cast<uint4 *>(outw)[k] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            if (lane == 0) outw[0] = pw;
+            __syncwarp();
 
             // ---------------- merge: private streams -> the tile's stream at their bit offsets ----------
             {

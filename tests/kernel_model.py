@@ -22,6 +22,7 @@ is spent.  See DESIGN.md "compress kernel" for the derivation.
 TILE = 1024
 SEG = 32
 MASK32 = 0xFFFFFFFF
+PRIV_WORDS = ((SEG - 1) * 9 + 15 + 31) // 32        # 31 nine-bit literals + one 15-bit match token
 
 
 def rev(v, n):
@@ -187,6 +188,7 @@ def phase_p3(tok, entries, bitbase, words):
         if fill:
             pw.append(acc & MASK32)          # fill < 32 here
         assert fill < 32
+        assert len(pw) <= PRIV_WORDS, (len(pw), total)      # the kernel's kPrivWords
         priv.append(pw)
         nbits.append(total)
     pos = bitbase

@@ -1,5 +1,6 @@
 """Parity of the CUDA compressor (through the C ABI) with the oracle / golden vectors."""
 import hashlib
+import os
 import zlib
 
 import numpy as np
@@ -83,6 +84,33 @@ def test_long_streams_one_fixed_block(engine, L):
         assert zlib.decompress(got) == data
 
 
+def worst_case_lane_blocks(n, rnd):
+    """Blocks of 9-bit literals (bytes >= 144) in which 4-byte repeats at distance 17..32 start at the last
+    position of a 32-position segment: a lane then emits 31 * 9 + 15 = 294 bits, the maximum."""
+    out = []
+    for _ in range(n):
+        b = bytearray(rnd.integers(144, 256, 2048, dtype=np.uint8).tobytes())
+        for p in range(63, 2040, 32):
+            if rnd.random() < 0.7:
+                d = int(rnd.integers(17, 33))
+                b[p:p + 4] = b[p - d:p - d + 4]
+        out.append(bytes(b))
+    return out
+
+
+def test_lane_private_stream_worst_case(engine):
+    """Regression: workload block 880395 makes one lane emit 289 bits (> 32 * 9); plus constructed
+    blocks that reach the 294-bit maximum in many lanes."""
+    rnd = np.random.default_rng(294)
+    blocks = [workload.block(880395, 2048)] + worst_case_lane_blocks(63, rnd)
+    arr = np.frombuffer(b"".join(blocks), dtype=np.uint8).reshape(len(blocks), 2048)
+    out, out_len, status = engine.compress_host(arr)
+    assert not status.any()
+    for i, b in enumerate(blocks):
+        assert out[i, :out_len[i]].tobytes() == hdlz_oracle.compress(b)[1], i
+        assert engine.compress(b) == hdlz_oracle.compress(b)[1]
+
+
 def test_worst_case_and_out_overflow(engine):
     data = bytes(np.random.default_rng(1).integers(144, 256, 2048, dtype=np.uint8))
     got = engine.compress(data)
@@ -121,8 +149,7 @@ def test_packed_host_round_trip(engine):
 
 def test_full_size_properties(engine):
     """BASELINE config 2 at full size (2^20 blocks x 2 KiB) on device memory: every stream is valid
-    zlib (round trip through the GPU inflater, byte compare on device) and a checksum of all output
-    lengths / a sampled byte compare matches the oracle."""
+    zlib (round trip through the GPU inflater, byte compare on device) and every stream equals the oracle's."""
     import torch
     n, L = 1 << 20, 2048
     ostride = compress_bound(L)
@@ -141,15 +168,17 @@ def test_full_size_properties(engine):
     h_in = d_in.view(n, L)[idx].cpu().numpy()
     for k, i in enumerate(idx):
         assert h_in[k].tobytes() == workload.block(i, L), i
-    # sampled byte-exactness against the oracle (stride sample of 4096 blocks)
-    sel = torch.arange(0, n, n // 4096, device=dev)
-    h_blocks = d_in.view(n, L)[sel].cpu().numpy()
-    h_out = d_out.view(n, ostride)[sel].cpu().numpy()
-    h_len = d_len[sel].cpu().numpy().astype(np.uint32)
-    want, want_len, _ = oracle_batch(h_blocks, np.full(len(sel), L, dtype=np.uint32))
-    assert np.array_equal(h_len, want_len)
-    mask = np.arange(ostride)[None, :] < h_len[:, None]
-    assert np.array_equal(h_out * mask, want * mask)
+    # byte-exactness of EVERY stream against the oracle, 65536 blocks at a time
+    # (a 1-in-2^20 block once exposed a sizing bug that a 4096-block sample missed)
+    step = 1 << 16
+    for first in range(0, n, step):
+        h_blocks = d_in.view(n, L)[first:first + step].cpu().numpy()
+        h_out = d_out.view(n, ostride)[first:first + step].cpu().numpy()
+        h_len = d_len[first:first + step].cpu().numpy().astype(np.uint32)
+        want, want_len, _ = oracle_batch(h_blocks, np.full(len(h_len), L, dtype=np.uint32), nthreads=os.cpu_count() or 8)
+        assert np.array_equal(h_len, want_len), first
+        mask = np.arange(ostride)[None, :] < h_len[:, None]
+        assert np.array_equal(h_out * mask, want * mask), first
     # encode -> decode round trip of ALL blocks on the device
     d_back = torch.empty(n * L, dtype=torch.uint8, device=dev)
     d_blen = torch.empty(n, dtype=torch.int32, device=dev)

@@ -109,5 +109,6 @@ def test_kernel_decomposition_model():
     cases += [workload.block(i, n) for i, n in enumerate([5, 6, 31, 32, 33, 63, 64, 65, 66, 67, 200, 2047, 2048, 2049,
                                                           2080, 2081, 4100])]
     cases += [bytes(rnd.choice(b"ab") for _ in range(n)) for n in (70, 2100)]
+    cases.append(workload.block(880395, 2048))          # a lane emits 289 bits (> 32 * 9): needs 10 private words
     for d in cases:
         assert kernel_model.compress(d) == hdlz_oracle.compress(d)[1], len(d)

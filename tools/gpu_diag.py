@@ -117,7 +117,7 @@ def main():
             log("ok   %s (L=%d -> %d)" % (name, len(data), len(got)))
     # batch
     small = os.environ.get('HDLZ_DIAG_SMALL') == '1'
-    nblk = 64 if small else 4096
+    nblk = 64 if small else int(os.environ.get('HDLZ_DIAG_BLOCKS', '4096'))
     if small:
         cases = cases[:12]
     blocks = workload.blocks(0, nblk, 2048)
@@ -126,14 +126,17 @@ def main():
     out, out_len, status = eng.compress_host(arr)
     log("batch %d blocks: %.3fs, status nonzero %d" % (nblk, time.time() - t, int((status != 0).sum())))
     nbad = 0
+    bad_idx = []
     for i in range(nblk):
         want = hdlz_oracle.compress(blocks[i])[1]
         got = out[i, :out_len[i]].tobytes()
         if got != want:
             nbad += 1
-            if nbad <= 3:
+            bad_idx.append(i)
+            if nbad <= 4:
                 log("FAIL batch block %d" % i)
                 explain(blocks[i], got, want, log)
+    log("bad block indices (first 40): %r" % (bad_idx[:40],))
     log("batch mismatches: %d / %d" % (nbad, nblk))
     bad += nbad
     # inflate
