@@ -26,7 +26,7 @@
 //            The same backward walk runs the parse DP: h[j] = skip count left for
 //            the next segment if a token starts at j (10-nibble shift register).
 //   phase P2 resolve the entry skip count of each of the 32 segments (greedy parse
-//            `di += match` / `di += 1`, deflate.py:960, 1008) with 32 shuffles.
+//            `di += match` / `di += 1`, deflate.py:960, 1008) with 32 broadcast loads of the published maps.
 //   phase P3 ONE forward walk per lane: the tokens that start in the segment are
 //            concatenated into a lane-private bitstream (put/do_flush, deflate.py:535-567);
 //            a warp scan of the bit counts gives every lane its offset, and a merge pass
