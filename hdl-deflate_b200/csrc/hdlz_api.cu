@@ -147,6 +147,8 @@ int hdlz_destroy(hdlz_ctx *c)
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_work) cudaFree(c->d_work);
     if (c->d_pack) cudaFree(c->d_pack);
+    for (int i = 0; i < 3; i++)
+        if (c->d_lane[i]) cudaFree(c->d_lane[i]);
     if (c->h_small) cudaFreeHost(c->h_small);
     delete c;
     return HDLZ_SUCCESS;
@@ -184,7 +186,7 @@ int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
     // hand-over list of the lane kernel: context-owned, so one decompress call per context at a time
     if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, inflate_work_words(n) * sizeof(uint32_t)))) return rc;
     return launch_inflate(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n,
-                          flags, ctx->d_work, (cudaStream_t)stream);
+                          flags, ctx->d_work, 0, (cudaStream_t)stream);
 }
 
 int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
@@ -259,7 +261,7 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
         for (uint64_t i = 1; i < n && ascending; i++) ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1];
     const uint64_t chunk = (in_off && !ascending) ? n : host_chunk(n, (in_off ? in_bytes / n + 1 : in_stride) + out_stride);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
-    if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, (inflate_work_words(n) + 16 * nchunks + 16) * sizeof(uint32_t))))
+    if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, (inflate_work_words(n) + 32 * nchunks + 32) * sizeof(uint32_t))))
         return rc;
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
@@ -277,7 +279,7 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
         HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off + first : nullptr,
                             in_stride, d_len + first, ctx->d_out + first * out_stride, out_stride, out_cap,
-                            d_olen + first, d_st + first, m, flags, ctx->d_work + first + 16 * (uint64_t)k, s);
+                            d_olen + first, d_st + first, m, flags, ctx->d_work + 2 * first + 32 * (uint64_t)k, k, s);
         if (rc) return rc;
         HDLZ_CUDA(cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
                                   cudaMemcpyDeviceToHost, s));

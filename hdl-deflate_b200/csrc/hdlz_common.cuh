@@ -10,6 +10,8 @@
 // internal routing flags of hdlz_decompress_batch (tests / profiling)
 #define HDLZ_F_FORCE_GENERAL 0x100u   /* warp-per-stream kernel only */
 #define HDLZ_F_FORCE_LANES 0x200u     /* lane-per-stream kernel first, whatever the batch size */
+#define HDLZ_F_PERSISTENT_LANES 0x800u /* fixed/stored lane kernel as a persistent grid (experiment) */
+#define HDLZ_F_NO_LANE_SCRATCH 0x400u /* lanes hand dynamic-block streams to the warp-per-stream kernel */
 
 struct hdlz_ctx {
     int device;
@@ -25,6 +27,8 @@ struct hdlz_ctx {
     size_t d_off_cap;
     uint8_t *d_pack;   // packed streams + per-chunk offsets/totals of hdlz_compress_host_packed
     size_t d_pack_cap;
+    void *d_lane[3];    // per-thread scratch of the lane inflater for dynamic blocks, one per concurrent launch
+    size_t d_lane_cap[3];
     uint64_t *h_small;  // pinned: per-chunk packed sizes
     size_t h_small_cap;
     uint32_t *d_work;  // [0] count, [4..] stream ids handed from the lane kernel to the warp kernel
@@ -53,9 +57,9 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
                    uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, uint32_t *d_work,
-                   cudaStream_t s);
+                   int lane_slot, cudaStream_t s);
 // words of device scratch launch_inflate needs for n streams (hand-over list of the lane kernel)
-inline size_t inflate_work_words(uint64_t n) { return (size_t)n + 8; }
+inline size_t inflate_work_words(uint64_t n) { return 2 * (size_t)n + 16; }
 int launch_pack(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
                 uint64_t *d_off, uint64_t *d_total, uint64_t n, cudaStream_t s);
 int launch_generate(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,

@@ -1,6 +1,7 @@
-// hdlz_inflate_lanes.cu — lane-per-stream inflater for batches of small streams made of fixed-
-// Huffman and stored blocks (what the reference's own compressor emits: one BTYPE=01 block per
-// stream, deflate.py:746-814; and zlib Z_FIXED streams, BASELINE config 3).
+// hdlz_inflate_lanes.cu — lane-per-stream inflater for batches of many streams: fixed-Huffman and
+// stored blocks (what the reference's own compressor emits: one BTYPE=01 block per stream,
+// deflate.py:746-814; zlib Z_FIXED streams, BASELINE config 3) and dynamic-Huffman blocks (zlib
+// level 6, BASELINE config 4; BL / READBL / REPEAT / HF1..HF4, deflate.py:1084-1400).
 //
 // Decode states NEXT / INFLATE / COPY of the reference (deflate.py:1402-1445, 1519-1659) with the
 // fixed tree (STATIC, :1064-1076; the `stat_leaves` LUT of :151-216 regenerated from RFC 1951):
@@ -15,8 +16,14 @@
 //     120 bytes — every match of the reference format (CWINDOW = 32) — and is flushed to HBM 32 bytes
 //     at a time (two 128-bit stores = whole sectors).  Longer distances read the flushed words back
 //     from global memory.
-//   - a stream that turns out to need the general decoder (dynamic block, unaligned buffers) is
-//     appended to a device work list that the warp-per-stream kernel (hdlz_inflate.cu) consumes.
+//   - the dynamic-capable instantiation is persistent: when all lanes of a warp are between streams
+//     they take their next 32 streams together;
+//   - dynamic blocks: every resident thread owns a 2.5 KiB scratch in global memory (9-bit literal/
+//     length and 8-bit distance primary tables + canonical arrays for longer codes) that stays
+//     L2-resident; the lane parses the block header and builds its tables by itself (plain scalar
+//     code, all lanes of a warp usually do it at the same time);
+//   - a stream the lanes cannot take (unaligned buffers, no scratch) is appended to a device work
+//     list that the warp-per-stream kernel (hdlz_inflate.cu) consumes.
 //
 // Algorithmic HBM traffic per stream: C bytes read + L bytes written.
 
@@ -32,7 +39,24 @@ int launch_inflate_general(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d
 namespace {
 
 constexpr int kLWarps = 4;
+constexpr int kLaneCtasPerSm = 10;     // fixed/stored instantiation (48 registers)
+constexpr int kDynCtasPerSm = 6;       // dynamic-capable instantiation (80 registers, 2.5 KiB of scratch per thread)
 constexpr int kRing = 32;   // words per lane (31 usable: the slot after the partial word is scratch)
+constexpr int kDynLitBits = 9;
+constexpr int kDynDistBits = 8;
+
+// per resident thread, global memory.  Table entry: (symbol << 4) | code length, 0 = longer code.
+struct LaneScratch {
+    uint16_t lit[1 << kDynLitBits];
+    uint16_t dist[1 << kDynDistBits];
+    uint16_t sorted_l[288];
+    uint16_t sorted_d[32];
+    uint16_t cnt_l[16];
+    uint16_t cnt_d[16];
+    uint8_t lens[320];
+};
+
+__constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 __constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35,
                                       43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -68,64 +92,130 @@ __device__ uint32_t fixed_dist_entry(uint32_t idx5)
     return (d < 2 ? 0u : (d >> 1) - 1u) | ((uint32_t)c_dbase[d] << 8);
 }
 
+// literal/length symbol -> the entry format of fixed_lit_entry without the code length
+__device__ uint32_t sym_entry(uint32_t sym)
+{
+    if (sym < 256) return sym << 16;
+    if (sym == 256) return 1u << 8;
+    if (sym > 285) return 3u << 8;
+    return ((uint32_t)c_lextra[sym - 257] << 4) | (2u << 8) | ((uint32_t)c_lbase[sym - 257] << 16);
+}
+
+// Canonical Huffman tables of one code (HF1INIT..HF4, SPREAD; deflate.py:1227-1400), built by ONE
+// thread in its scratch.  Returns 0, or 1 for an over-subscribed / illegally incomplete code
+// (zlib's inflate_table rules).
+__device__ __noinline__ int lane_build(const uint8_t *lens, int nsym, uint16_t *tbl, int tbits, uint16_t *cnt,
+                                       uint16_t *sorted, bool allow_incomplete)
+{
+    uint16_t first[16], offs[16], run[16];
+    for (int l = 0; l < 16; ++l) { cnt[l] = 0; run[l] = 0; }
+    for (int s = 0; s < nsym; ++s) cnt[lens[s]]++;
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(tbl);
+    for (int i = 0; i < (1 << tbits) / 2; ++i) t32[i] = 0;
+    int left = 1, maxlen = 0;
+    for (int l = 1; l <= 15; ++l) {
+        const int c = cnt[l];
+        left = 2 * left - c;
+        if (c) maxlen = l;
+        if (left < 0) return 1;
+    }
+    if (maxlen == 0) return 0;                 // no codes: any use fails later
+    if (left > 0 && !(allow_incomplete && maxlen == 1)) return 1;
+    uint32_t code = 0, off = 0;
+    for (int l = 1; l <= 15; ++l) {
+        first[l] = (uint16_t)code;
+        offs[l] = (uint16_t)off;
+        code = (code + cnt[l]) << 1;
+        off += cnt[l];
+    }
+    for (int s = 0; s < nsym; ++s) {
+        const uint32_t l = lens[s];
+        if (!l) continue;
+        const uint32_t k = run[l]++;
+        sorted[offs[l] + k] = (uint16_t)s;
+        if ((int)l <= tbits) {
+            const uint32_t rev = __brev(first[l] + k) >> (32 - l);
+            const uint16_t ent = (uint16_t)((s << 4) | l);
+            for (uint32_t idx = rev; idx < (1u << tbits); idx += 1u << l) tbl[idx] = ent;
+        }
+    }
+    return 0;
+}
+
+// code longer than the primary table: canonical decode one bit at a time.  -> (sym << 4) | len, 0 = invalid
+__device__ __noinline__ uint32_t lane_slow_decode(uint32_t bits, const uint16_t *cnt, const uint16_t *sorted)
+{
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; ++l) {
+        code |= (int)((bits >> (l - 1)) & 1u);
+        const int c = cnt[l];
+        if (code - c < first) return ((uint32_t)sorted[index + (code - first)] << 4) | (uint32_t)l;
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return 0;
+}
+
+// kDyn = false: fixed / stored blocks only (lean: fewer registers, more resident warps); a stream
+//                with a dynamic block is appended to `dyn_list`.  Items: all n_streams.
+// kDyn = true : everything; items come from `items[0 .. *item_count)` (the list the first
+//                instantiation filled).  Either way unaligned streams go to `work_list`.
+template <bool kDyn>
 __global__ void __launch_bounds__(kLWarps * 32)
 k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint64_t in_stride,
                 const uint32_t *__restrict__ in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
                 uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, uint32_t flags,
-                uint32_t *__restrict__ work_list, uint32_t *__restrict__ work_count)
+                uint32_t *__restrict__ work_list, uint32_t *__restrict__ work_count,
+                uint32_t *__restrict__ dyn_list, uint32_t *__restrict__ dyn_count,
+                const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, LaneScratch *scratch)
 {
-    __shared__ uint32_t s_lit[512];
-    __shared__ uint32_t s_dist[32];
+    const uint64_t n_items = items ? (uint64_t)*item_count : n_streams;
+    if (n_items == 0) return;
+    __shared__ uint32_t s_lit[512];       // fixed tree: 9 stream bits -> entry (see fixed_lit_entry)
+    __shared__ uint32_t s_dist[32];       // fixed tree: 5 stream bits -> distance entry
+    __shared__ uint32_t s_sym[288];       // literal/length symbol -> entry without code length
+    __shared__ uint32_t s_dsym[32];       // distance symbol -> distance entry
     __shared__ uint32_t s_ring[kLWarps][kRing][32];
 
     for (int i = threadIdx.x; i < 512; i += kLWarps * 32) s_lit[i] = fixed_lit_entry((uint32_t)i);
-    if (threadIdx.x < 32) s_dist[threadIdx.x] = fixed_dist_entry(threadIdx.x);
+    for (int i = threadIdx.x; i < 288; i += kLWarps * 32) s_sym[i] = sym_entry((uint32_t)i);
+    if (threadIdx.x < 32) {
+        s_dist[threadIdx.x] = fixed_dist_entry(threadIdx.x);
+        s_dsym[threadIdx.x] = fixed_dist_entry(__brev(threadIdx.x) >> 27);
+    }
     __syncthreads();
 
-    // per-lane decoder state.  The warp iterates in lock step: every trip of the main loop each live
-    // lane decodes ONE symbol (and performs its copy); the vote that controls the loop is the
-    // reconvergence point, so lanes that took the literal and the match branch meet again each trip.
-    enum { S_HEADER = 0, S_FIXED = 1, S_STORED = 2, S_DONE = 3 };
+    // per-lane decoder state machine.  The warp iterates in lock step: the vote that controls the
+    // loop is the reconvergence point, so lanes that took different branches meet again each trip.
+    enum { S_IDLE = 0, S_HEADER = 1, S_FIXED = 2, S_STORED = 3, S_DYN = 4, S_FINISH = 5, S_DONE = 6 };
 
-    const uint64_t sid = (uint64_t)blockIdx.x * (kLWarps * 32) + threadIdx.x;
-    const bool valid = sid < n_streams;
+    const uint64_t n_threads = (uint64_t)gridDim.x * (kLWarps * 32);
+    const uint64_t gtid = (uint64_t)blockIdx.x * (kLWarps * 32) + threadIdx.x;
+    uint64_t next_item = gtid;
+    uint64_t sid = 0;
     uint32_t *ring = &s_ring[threadIdx.x >> 5][0][threadIdx.x & 31];     // word k at ring[k * 32]
+    LaneScratch *my = (kDyn && scratch) ? scratch + gtid : nullptr;
+    bool to_dyn = false;            // hand this stream to the dynamic-capable instantiation
 
-    const uint32_t n_in = valid ? in_len[sid] : 0;
-    const uint8_t *src = in + (valid ? (in_off ? in_off[sid] : sid * in_stride) : 0);
-    uint8_t *dst = out + (valid ? sid * out_stride : 0);
-    uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst);
-    const uint32_t *inw = reinterpret_cast<const uint32_t *>(src);
+    const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) != 0;
+    uint32_t state = S_IDLE;
 
+    // per-stream state
+    uint32_t n_in = 0, nfull = 0;
+    const uint8_t *src = in;
+    uint8_t *dst = out;
+    uint32_t *dst32 = reinterpret_cast<uint32_t *>(out);
+    const uint32_t *inw = reinterpret_cast<const uint32_t *>(in);
     uint32_t st = HDLZ_OK;
     bool hand_over = false;
     uint32_t o = 0, cw = 0, flushed = 0;
     uint32_t ad_a = 1, ad_b = 0, ad_n = 0;
-    const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) != 0;
-    uint32_t state = S_HEADER;
-
-    if (!valid) {
-        state = S_DONE;
-    } else if ((reinterpret_cast<uintptr_t>(src) & 3u) || (reinterpret_cast<uintptr_t>(dst) & 15u)) {
-        hand_over = true;                              // the warp-per-stream kernel takes any alignment
-        state = S_DONE;
-    } else if (n_in < 2) {
-        st = HDLZ_ST_TRUNCATED;
-        state = S_DONE;
-    } else if (flags & HDLZ_F_VERIFY_HEADER) {
-        const uint32_t cmf = src[0], flg = src[1];
-        if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u || (flg & 0x20u)) {
-            st = HDLZ_ST_BAD_HEADER;
-            state = S_DONE;
-        }
-    }
-
-    const uint32_t nfull = n_in >> 2;
-    uint32_t wi = 1;
+    uint32_t wi = 1, fill = 16, final_blk = 0, stored_left = 0;
     uint64_t acc = 0;
-    uint32_t fill = 16;
-    uint32_t final_blk = 0;
-    uint32_t stored_left = 0;
+    uint32_t rem = 0, dist = 1;      // bytes still to copy of the current match, its distance
+    uint32_t trip = 0;
 
     auto load_word = [&](uint32_t w) -> uint32_t {
         if (w < nfull) return __ldg(inw + w);
@@ -146,14 +236,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             if (++ad_n == 5552) { ad_a %= 65521u; ad_b %= 65521u; ad_n = 0; }
         }
     };
-    // Output word x: the ring always holds the last kRing words INCLUDING the partial word being
-    // filled, so recent data needs no special case; older words come back from global memory
-    // (they were flushed: a 32-byte group is stored as soon as its last word completes).
-    auto fetch = [&](uint32_t x, uint32_t wo) -> uint32_t {
-        if (wo - x < (uint32_t)(kRing - 1)) return ring[(x & (kRing - 1)) * 32];
-        return dst32[x];
-    };
-    // Store 32 completed bytes (two 128-bit stores = whole sectors) if this lane has them.
+    // Store 32 completed bytes (two 128-bit stores = whole sectors) while this lane has them.
     // Called at converged points of the loop; `flushed` counts the words already in global memory.
     auto flush8 = [&]() {
         while ((o >> 2) - flushed >= 8u) {
@@ -178,51 +261,85 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         ring[((wo + 1u) & (kRing - 1)) * 32] = (uint32_t)(comb >> 32);
         cw = ob + m >= 4u ? (uint32_t)(comb >> 32) : (uint32_t)comb;
     };
-    // bytes s .. s+3 of the output for a back-reference of distance `dist` (s = o - dist)
-    auto source = [&](uint32_t dist) -> uint32_t {
-        const uint32_t s = o - dist;
+    // bytes s .. s+3 of the output for a back-reference of distance `d` (s = o - d).  The ring always
+    // holds the last kRing - 1 words including the partial one; older words were flushed and come
+    // back from global memory.
+    auto source = [&](uint32_t d) -> uint32_t {
+        const uint32_t s = o - d;
         const uint32_t ws = s >> 2, wo = o >> 2;
         uint32_t w0, w1;
-        if (wo - ws < (uint32_t)(kRing - 1)) {         // both words are in the ring (ws + 1 <= wo + 1: scratch slot)
+        if (wo - ws < (uint32_t)(kRing - 1)) {
             w0 = ring[(ws & (kRing - 1)) * 32];
             w1 = ring[((ws + 1u) & (kRing - 1)) * 32];
-        } else {                                       // far back-reference: flushed long ago
+        } else {
             w0 = dst32[ws];
             w1 = dst32[ws + 1u];
         }
         const uint32_t v = __funnelshift_r(w0, w1, 8u * (s & 3u));
-        // distance < 4: the source overlaps what is being written -> period-`dist` pattern:
-        // keep the first `dist` bytes and replicate them with one multiply
-        const uint32_t dd = dist < 4u ? dist : 4u;
+        // distance < 4: the source overlaps what is being written -> period-`d` pattern:
+        // keep the first `d` bytes and replicate them with one multiply
+        const uint32_t dd = d < 4u ? d : 4u;
         const uint32_t keep = 0xFFFFFFFFu >> ((32u - 8u * dd) & 31u);   // dd == 0 only on lanes that are not copying
         const uint32_t mult = dd == 4u ? 1u : dd == 3u ? 0x01000001u : dd == 2u ? 0x00010001u : 0x01010101u;
         return (v & keep) * mult;
     };
-
-    if (state != S_DONE) {
-        acc = (uint64_t)(load_word(0) >> 16);          // skip the zlib header: di = 2 (deflate.py:644)
-        ring[0] = 0;
-    }
-
-    uint32_t rem = 0, dist = 1;      // bytes still to copy of the current match, its distance
-    uint32_t trip = 0;
+    auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
 
     while (__any_sync(HDLZ_FULL_MASK, state != S_DONE)) {
         // every 8 trips (a trip appends at most 4 bytes, so at most 8 words accumulate) all lanes
         // store their completed 32-byte groups together
         if ((++trip & 7u) == 0) flush8();
+
+        // ---- when every lane of the warp is between streams, all take their next stream together
+        // (a per-lane refetch would run this and the block header with one or two active lanes)
+        if (__all_sync(HDLZ_FULL_MASK, state == S_IDLE || state == S_DONE)) {
+            if (state == S_IDLE) {
+            if (next_item >= n_items) {
+                state = S_DONE;
+            } else {
+                sid = items ? (uint64_t)items[next_item] : next_item;
+                next_item += n_threads;
+                to_dyn = false;
+                n_in = in_len[sid];
+                src = in + (in_off ? in_off[sid] : sid * in_stride);
+                dst = out + sid * out_stride;
+                dst32 = reinterpret_cast<uint32_t *>(dst);
+                inw = reinterpret_cast<const uint32_t *>(src);
+                nfull = n_in >> 2;
+                st = HDLZ_OK;
+                hand_over = false;
+                o = 0; cw = 0; flushed = 0;
+                ad_a = 1; ad_b = 0; ad_n = 0;
+                wi = 1; fill = 16; final_blk = 0; stored_left = 0; rem = 0; dist = 1;
+                state = S_HEADER;
+                if ((reinterpret_cast<uintptr_t>(src) & 3u) || (reinterpret_cast<uintptr_t>(dst) & 15u)) {
+                    hand_over = true;                  // the warp-per-stream kernel takes any alignment
+                    state = S_FINISH;
+                } else if (n_in < 2) {
+                    fail(HDLZ_ST_TRUNCATED);
+                } else if (flags & HDLZ_F_VERIFY_HEADER) {
+                    const uint32_t cmf = src[0], flg = src[1];
+                    if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u || (flg & 0x20u))
+                        fail(HDLZ_ST_BAD_HEADER);
+                }
+                if (state == S_HEADER) {
+                    acc = (uint64_t)(load_word(0) >> 16);      // skip the zlib header: di = 2 (deflate.py:644)
+                    ring[0] = 0;
+                }
+            }
+            }
+        }
+
         if (state == S_FIXED) {
             // ---- fixed block (NEXT / INFLATE / COPY): every trip appends at most four bytes ----
             // A lane either continues the copy it is in (rem != 0) or decodes: up to four
             // consecutive literals (packed into one append), or one match / end-of-block code.
             if (fill < 32) {
-                if (wi > nfull + 2) { st = HDLZ_ST_TRUNCATED; state = S_DONE; }
+                if (wi > nfull + 2) fail(HDLZ_ST_TRUNCATED);
                 else refill();
             }
             const bool decode = state == S_FIXED && rem == 0;
             const uint32_t room = out_cap - o;                       // o <= out_cap always
-            // literal run: symbol j is taken while everything before it was a literal, its code
-            // fits in the 32 valid bits, and the output has room
             uint32_t used = 0, lits = 0, nlit = 0;
             const uint32_t a32 = (uint32_t)acc;                      // >= 32 valid bits
             const uint32_t e0 = s_lit[a32 & 511u];
@@ -252,20 +369,18 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 const uint32_t dnew = (de >> 8) + ((x2 >> 5) & ((1u << deb) - 1u));
                 if (kind == 2u) {
                     used = nb + eb + 5u + deb;
-                    if (deb == 15u) { st = HDLZ_ST_BAD_CODE; state = S_DONE; }
-                    else if (dnew > o) { st = HDLZ_ST_DIST_TOO_FAR; state = S_DONE; }     // "distance too big" (deflate.py:1506-1508)
-                    else if (len > room) { st = HDLZ_ST_OUT_OVERFLOW; state = S_DONE; }
+                    if (deb == 15u) fail(HDLZ_ST_BAD_CODE);
+                    else if (dnew > o) fail(HDLZ_ST_DIST_TOO_FAR);         // "distance too big" (deflate.py:1506-1508)
+                    else if (len > room) fail(HDLZ_ST_OUT_OVERFLOW);
                     else { rem = len; dist = dnew; }
                 } else if (kind == 1u) {
                     used = nb;
-                    state = final_blk ? S_DONE : S_HEADER;          // end of block
-                    if (final_blk) final_blk = 2;                   // 2 = finished cleanly
+                    state = final_blk ? S_FINISH : S_HEADER;                // end of block
+                    if (final_blk) final_blk = 2;                           // 2 = finished cleanly
                 } else if (kind == 0u) {
-                    st = HDLZ_ST_OUT_OVERFLOW;                      // a literal with no room left
-                    state = S_DONE;
+                    fail(HDLZ_ST_OUT_OVERFLOW);                             // a literal with no room left
                 } else {
-                    st = HDLZ_ST_BAD_CODE;                          // "invalid token" (deflate.py:1559-1560)
-                    state = S_DONE;
+                    fail(HDLZ_ST_BAD_CODE);                                 // "invalid token" (deflate.py:1559-1560)
                 }
             }
             acc >>= used; fill -= used;
@@ -274,7 +389,75 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             const uint32_t sv = source(copying ? dist : 0u);
             const uint32_t m = copying ? (rem < 4u ? rem : 4u) : nlit;
             rem -= copying ? m : 0u;
-            if (m && state != S_DONE) append(copying ? sv : lits, m);
+            if (m && st == HDLZ_OK) append(copying ? sv : lits, m);
+        } else if (kDyn && state == S_DYN) {
+            // ---- dynamic block: the same trip structure, tables in this lane's global scratch ----
+            if (rem == 0) {
+                if (fill < 32) {
+                    if (wi > nfull + 2) fail(HDLZ_ST_TRUNCATED);
+                    else refill();
+                }
+                if (state == S_DYN) {
+                    const uint32_t room = out_cap - o;
+                    uint32_t lits = 0, nlit = 0, used = 0;
+                    uint32_t e = 0;
+                    // up to four literals (or stop at the first other symbol)
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t x = (uint32_t)(acc >> used);
+                        e = my->lit[x & ((1u << kDynLitBits) - 1u)];
+                        if ((e & 15u) == 0) e = lane_slow_decode(x, my->cnt_l, my->sorted_l);
+                        const uint32_t nb = e & 15u;
+                        if (nb == 0 || (e >> 4) >= 256u || used + nb > 32u || nlit >= room) break;
+                        lits |= (e >> 4) << (8 * k);
+                        used += nb;
+                        ++nlit;
+                        e = 0xFFFFFFFFu;                                    // consumed
+                    }
+                    acc >>= used; fill -= used;
+                    if (nlit) {
+                        append(lits, nlit);
+                    } else if ((e & 15u) == 0) {
+                        fail(HDLZ_ST_BAD_CODE);                             // no such code
+                    } else {
+                        const uint32_t nb = e & 15u, info = s_sym[e >> 4];
+                        const uint32_t kind = (info >> 8) & 3u;
+                        if (kind == 0u) {
+                            fail(HDLZ_ST_OUT_OVERFLOW);                     // a literal with no room left
+                        } else if (kind == 1u) {
+                            acc >>= nb; fill -= nb;
+                            state = final_blk ? S_FINISH : S_HEADER;
+                            if (final_blk) final_blk = 2;
+                        } else if (kind == 3u) {
+                            fail(HDLZ_ST_BAD_CODE);
+                        } else {
+                            const uint32_t eb = (info >> 4) & 15u;
+                            if (fill < nb + eb) refill();
+                            const uint32_t len = (info >> 16) + ((uint32_t)(acc >> nb) & ((1u << eb) - 1u));
+                            acc >>= nb + eb; fill -= nb + eb;
+                            if (fill < 32) refill();
+                            const uint32_t y = (uint32_t)acc;
+                            uint32_t d = my->dist[y & ((1u << kDynDistBits) - 1u)];
+                            if ((d & 15u) == 0) d = lane_slow_decode(y, my->cnt_d, my->sorted_d);
+                            const uint32_t dnb = d & 15u;
+                            const uint32_t de = s_dsym[(d >> 4) & 31u];
+                            const uint32_t deb = de & 15u;
+                            if (dnb == 0 || (d >> 4) >= 30u) fail(HDLZ_ST_BAD_CODE);
+                            else {
+                                const uint32_t dnew = (de >> 8) + ((uint32_t)(acc >> dnb) & ((1u << deb) - 1u));
+                                acc >>= dnb + deb; fill -= dnb + deb;        // <= 15 + 13 = 28 bits
+                                if (dnew > o) fail(HDLZ_ST_DIST_TOO_FAR);
+                                else if (len > room) fail(HDLZ_ST_OUT_OVERFLOW);
+                                else { rem = len; dist = dnew; }
+                            }
+                        }
+                    }
+                }
+            }
+            if (state == S_DYN && rem != 0) {
+                const uint32_t m = rem < 4u ? rem : 4u;
+                append(source(dist), m);
+                rem -= m;
+            }
         } else if (state == S_HEADER) {
             if (fill < 32) refill();
             final_blk = (uint32_t)acc & 1u;
@@ -282,15 +465,9 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             acc >>= 3; fill -= 3;
             if (type == 1) {
                 state = S_FIXED;
-            } else if (type == 2) {
-                // dynamic block: this stream belongs to the general decoder, which restarts it
-                // from its first byte (anything produced so far is simply rewritten)
-                hand_over = true;
-                state = S_DONE;
             } else if (type == 3) {
-                st = HDLZ_ST_BAD_BTYPE;                             // "Bad method" (deflate.py:718-721)
-                state = S_DONE;
-            } else {
+                fail(HDLZ_ST_BAD_BTYPE);                                    // "Bad method" (deflate.py:718-721)
+            } else if (type == 0) {
                 // stored block header (deflate.py:709-717)
                 const uint32_t drop = fill & 7u;
                 acc >>= drop; fill -= drop;
@@ -298,10 +475,66 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 const uint32_t len = (uint32_t)acc & 0xFFFFu, nlen = ((uint32_t)acc >> 16) & 0xFFFFu;
                 acc >>= 32; fill -= 32;
                 const uint64_t bytepos = ((uint64_t)wi * 32 - fill) >> 3;
-                if ((len ^ 0xFFFFu) != nlen) { st = HDLZ_ST_BAD_STORED; state = S_DONE; }
-                else if (bytepos + len > n_in) { st = HDLZ_ST_TRUNCATED; state = S_DONE; }
-                else if ((uint64_t)o + len > out_cap) { st = HDLZ_ST_OUT_OVERFLOW; state = S_DONE; }
+                if ((len ^ 0xFFFFu) != nlen) fail(HDLZ_ST_BAD_STORED);
+                else if (bytepos + len > n_in) fail(HDLZ_ST_TRUNCATED);
+                else if ((uint64_t)o + len > out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
                 else { stored_left = len; state = S_STORED; }
+            } else if (!kDyn || !my) {
+                // dynamic block: another decoder restarts the stream from its first byte (anything
+                // produced so far is simply rewritten) — the dynamic-capable lanes, or without
+                // scratch the warp-per-stream kernel
+                hand_over = true;
+                to_dyn = !kDyn && dyn_list != nullptr;
+                state = S_FINISH;
+            } else if (kDyn) {
+                // ---- dynamic block header (BL / READBL / REPEAT, deflate.py:1084-1202) ----
+                auto get = [&](uint32_t n) -> uint32_t {                    // n <= 16
+                    if (fill < n) refill();
+                    const uint32_t v = (uint32_t)acc & ((1u << n) - 1u);
+                    acc >>= n; fill -= n;
+                    return v;
+                };
+                const uint32_t nlen = get(5) + 257, ndist = get(5) + 1, ncode = get(4) + 4;
+                uint32_t bad = (nlen > 286 || ndist > 30) ? 1u : 0u;
+                uint8_t *lens = my->lens;
+                for (int i = 0; i < 19; ++i) lens[i] = 0;
+                for (uint32_t i = 0; i < ncode; ++i) lens[c_clorder[i]] = (uint8_t)get(3);
+                // code-length code: 7-bit table in the (not yet built) distance table area
+                if (!bad) bad = lane_build(lens, 19, my->dist, 7, my->cnt_d, my->sorted_d, false);
+                if (!bad) {
+                    uint32_t any = 0;
+                    for (int l = 1; l <= 7; ++l) any |= my->cnt_d[l];
+                    if (!any) bad = 1;
+                }
+                uint8_t *ll = my->lens;                                     // literal/length + distance lengths
+                uint32_t idx = 0, prev = 0;
+                const uint32_t total = nlen + ndist;
+                // the 19 code-length lengths are dead once their table is built: reuse the array
+                while (!bad && idx < total) {
+                    if (fill < 32) {
+                        if (wi > nfull + 2) { bad = 2; break; }
+                        refill();
+                    }
+                    const uint32_t e = my->dist[(uint32_t)acc & 127u];
+                    const uint32_t nb = e & 15u, sym = e >> 4;
+                    if (nb == 0) { bad = 1; break; }
+                    acc >>= nb; fill -= nb;
+                    uint32_t rep, val;
+                    if (sym < 16) { rep = 1; val = sym; prev = sym; }
+                    else if (sym == 16) {
+                        if (idx == 0) { bad = 1; break; }
+                        rep = 3 + get(2); val = prev;
+                    } else if (sym == 17) { rep = 3 + get(3); val = 0; prev = 0; }
+                    else { rep = 11 + get(7); val = 0; prev = 0; }
+                    if (idx + rep > total) { bad = 1; break; }
+                    for (uint32_t k = 0; k < rep; ++k) ll[idx + k] = (uint8_t)val;
+                    idx += rep;
+                }
+                if (!bad && ll[256] == 0) bad = 1;                           // no end-of-block code
+                if (!bad) bad = lane_build(ll + nlen, (int)ndist, my->dist, kDynDistBits, my->cnt_d, my->sorted_d, true);
+                if (!bad) bad = lane_build(ll, (int)nlen, my->lit, kDynLitBits, my->cnt_l, my->sorted_l, true);
+                if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
+                else state = S_DYN;
             }
         } else if (state == S_STORED) {
             // stored bytes, up to 4 per trip (COPY with method 0, deflate.py:1603-1616)
@@ -311,39 +544,39 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 acc >>= 8; fill -= 8;
             }
             if (stored_left == 0) {
-                state = final_blk ? S_DONE : S_HEADER;
+                state = final_blk ? S_FINISH : S_HEADER;
                 if (final_blk) final_blk = 2;
             }
-        }
-    }
-
-    if (valid && st == HDLZ_OK && !hand_over) {
-        if (final_blk != 2) {
-            st = HDLZ_ST_TRUNCATED;
-        } else {
-            // words completed since the last 32-byte flush, then the bytes of the partial word
-            const uint32_t wo = o >> 2;
-            for (uint32_t x = flushed; x < wo; ++x) dst32[x] = ring[(x & (kRing - 1)) * 32];
-            for (uint32_t k = 0; k < (o & 3u); ++k) dst[(o & ~3u) + k] = (uint8_t)(cw >> (8 * k));
-            const uint64_t bp = (uint64_t)wi * 32 - fill;
-            const uint64_t tp = (bp + 7) >> 3;                       // Adler-32 trailer must be present
-            if (bp > 8ull * n_in || tp + 4 > n_in) {
-                st = HDLZ_ST_TRUNCATED;                              // "NO EOF!" (deflate.py:1535-1539)
-            } else if (want_adler) {
-                ad_a %= 65521u; ad_b %= 65521u;
-                const uint32_t want = ((uint32_t)src[tp] << 24) | ((uint32_t)src[tp + 1] << 16) |
-                                      ((uint32_t)src[tp + 2] << 8) | src[tp + 3];
-                if (((ad_b << 16) | ad_a) != want) st = HDLZ_ST_BAD_ADLER;
+        } else if (state == S_FINISH) {
+            // ---- end of a stream: tail of the output, trailer checks, result words ----
+            if (st == HDLZ_OK && !hand_over) {
+                if (final_blk != 2) {
+                    st = HDLZ_ST_TRUNCATED;
+                } else {
+                    const uint32_t wo = o >> 2;
+                    for (uint32_t x = flushed; x < wo; ++x) dst32[x] = ring[(x & (kRing - 1)) * 32];
+                    for (uint32_t k = 0; k < (o & 3u); ++k) dst[(o & ~3u) + k] = (uint8_t)(cw >> (8 * k));
+                    const uint64_t bp = (uint64_t)wi * 32 - fill;
+                    const uint64_t tp = (bp + 7) >> 3;                       // Adler-32 trailer must be present
+                    if (bp > 8ull * n_in || tp + 4 > n_in) {
+                        st = HDLZ_ST_TRUNCATED;                              // "NO EOF!" (deflate.py:1535-1539)
+                    } else if (want_adler) {
+                        ad_a %= 65521u; ad_b %= 65521u;
+                        const uint32_t want = ((uint32_t)src[tp] << 24) | ((uint32_t)src[tp + 1] << 16) |
+                                              ((uint32_t)src[tp + 2] << 8) | src[tp + 3];
+                        if (((ad_b << 16) | ad_a) != want) st = HDLZ_ST_BAD_ADLER;
+                    }
+                }
             }
+            if (hand_over) {
+                if (to_dyn) dyn_list[atomicAdd(dyn_count, 1u)] = (uint32_t)sid;
+                else work_list[atomicAdd(work_count, 1u)] = (uint32_t)sid;
+            } else {
+                out_len[sid] = st == HDLZ_OK ? o : 0;
+                if (status) status[sid] = st;
+            }
+            state = S_IDLE;
         }
-    }
-
-    if (!valid) return;
-    if (hand_over) {
-        work_list[atomicAdd(work_count, 1u)] = (uint32_t)sid;
-    } else {
-        out_len[sid] = st == HDLZ_OK ? o : 0;
-        if (status) status[sid] = st;
     }
 }
 
@@ -352,7 +585,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
                    uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, uint32_t *d_work,
-                   cudaStream_t s)
+                   int lane_slot, cudaStream_t s)
 {
     if (n == 0) return HDLZ_SUCCESS;
     // Few streams: one warp each is the better mapping.  Many streams: one lane each first,
@@ -362,13 +595,39 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
     if (!lanes_first)
         return launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
                                       d_status, n, flags, nullptr, nullptr, s);
-    uint32_t *count = d_work, *list = d_work + 8;
-    HDLZ_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
-    const uint64_t blocks = (n + kLWarps * 32 - 1) / (kLWarps * 32);
-    k_inflate_lanes<<<(unsigned)blocks, kLWarps * 32, 0, s>>>(d_in, d_in_off, in_stride, d_in_len, d_out, out_stride,
-                                                              out_cap, d_out_len, d_status, n, flags, list, count);
+    // d_work: [0] count of streams for the warp-per-stream kernel, [1] count of streams with dynamic
+    // blocks, [16 ..) the two lists (n entries each)
+    uint32_t *count = d_work, *dyn_count = d_work + 1, *list = d_work + 16, *dyn_list = d_work + 16 + n;
+    HDLZ_CUDA(cudaMemsetAsync(d_work, 0, 2 * sizeof(uint32_t), s));
+    uint64_t blocks = (n + kLWarps * 32 - 1) / (kLWarps * 32);
+    if (flags & HDLZ_F_PERSISTENT_LANES) {
+        const uint64_t resident = (uint64_t)ctx->sm_count * kLaneCtasPerSm;
+        if (blocks > resident) blocks = resident;
+    }
+    // scratch for dynamic blocks: one slot per concurrent launch (the *_host pipelines run three)
+    const int slot = lane_slot % 3;
+    const uint64_t dyn_blocks = (uint64_t)ctx->sm_count * kDynCtasPerSm;
+    const size_t need = (size_t)dyn_blocks * (kLWarps * 32) * sizeof(LaneScratch);
+    if (!(flags & HDLZ_F_NO_LANE_SCRATCH) && ctx->d_lane_cap[slot] < need) {
+        if (ctx->d_lane[slot]) HDLZ_CUDA(cudaFree(ctx->d_lane[slot]));
+        ctx->d_lane[slot] = nullptr;
+        ctx->d_lane_cap[slot] = 0;
+        if (cudaMalloc(&ctx->d_lane[slot], need) == cudaSuccess) ctx->d_lane_cap[slot] = need;
+        else (void)cudaGetLastError();           // no scratch: dynamic streams go to the warp-per-stream kernel
+    }
+    LaneScratch *scratch = (flags & HDLZ_F_NO_LANE_SCRATCH) ? nullptr : reinterpret_cast<LaneScratch *>(ctx->d_lane[slot]);
+    k_inflate_lanes<false><<<(unsigned)blocks, kLWarps * 32, 0, s>>>(
+        d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n, flags, list, count,
+        scratch ? dyn_list : nullptr, dyn_count, nullptr, nullptr, nullptr);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
+    if (scratch) {
+        k_inflate_lanes<true><<<(unsigned)dyn_blocks, kLWarps * 32, 0, s>>>(
+            d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n, flags, list, count,
+            nullptr, nullptr, dyn_list, dyn_count, scratch);
+        ctx->launches++;
+        HDLZ_CUDA(cudaGetLastError());
+    }
     return launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
                                   d_status, n, flags, list, count, s);
 }

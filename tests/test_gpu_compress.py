@@ -111,6 +111,53 @@ def test_lane_private_stream_worst_case(engine):
         assert engine.compress(b) == hdlz_oracle.compress(b)[1]
 
 
+def test_randomized_shapes_match_oracle(engine):
+    """4000 streams of random length (5..6000) and shape — text, two-symbol, runs, ramps, random, random+repeat,
+    period-d patterns for every d in 1..40 — in one strided batch and one packed batch."""
+    rnd = np.random.default_rng(20261017)
+    n, stride = 4000, 6016
+    arr = np.zeros((n, stride), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint32)
+    text = np.frombuffer((" ".join("   Hello World! %d     " % i for i in range(400))).encode(), dtype=np.uint8)
+    for i in range(n):
+        L = int(rnd.choice([5, 6, 31, 32, 33, 1023, 1024, 1025, 1055, 1056, 1057, 2048, 6000])) if i % 5 == 0 \
+            else int(rnd.integers(5, 6001))
+        kind = i % 8
+        if kind == 0:
+            d = text[:L] if L <= len(text) else np.resize(text, L)
+        elif kind == 1:
+            d = rnd.integers(97, 99, L, dtype=np.uint8)
+        elif kind == 2:
+            d = np.repeat(rnd.integers(0, 256, L // 7 + 1, dtype=np.uint8), 7)[:L]
+        elif kind == 3:
+            d = (np.arange(L) % 256).astype(np.uint8)
+        elif kind == 4:
+            d = rnd.integers(0, 256, L, dtype=np.uint8)
+        elif kind == 5:
+            d = np.frombuffer(workload.block(i, L), dtype=np.uint8)
+        elif kind == 6:
+            per = 1 + i % 40
+            d = np.resize(rnd.integers(0, 256, per, dtype=np.uint8), L)
+        else:
+            d = rnd.integers(144, 256, L, dtype=np.uint8)
+            d[L // 2:] = d[:L - L // 2]
+        arr[i, :L] = d
+        lens[i] = L
+    want = [hdlz_oracle.compress(arr[i, :lens[i]].tobytes())[1] for i in range(n)]
+    out, out_len, status = engine.compress_host(arr, lens)
+    assert not status.any()
+    for i in range(n):
+        assert out[i, :out_len[i]].tobytes() == want[i], (i, lens[i], i % 8)
+    packed, off, plen, pst = engine.compress_host_packed(arr, lens)
+    assert not pst.any() and np.array_equal(plen, out_len)
+    for i in range(0, n, 7):
+        assert packed[int(off[i]):int(off[i]) + int(plen[i])].tobytes() == want[i], i
+    back, blen, bst = engine.decompress_host(packed, plen, 6000, in_off=off, flags=3)
+    assert not bst.any() and np.array_equal(blen, lens)
+    for i in range(0, n, 3):
+        assert back[i, :lens[i]].tobytes() == arr[i, :lens[i]].tobytes(), i
+
+
 def test_worst_case_and_out_overflow(engine):
     data = bytes(np.random.default_rng(1).integers(144, 256, 2048, dtype=np.uint8))
     got = engine.compress(data)

@@ -71,10 +71,11 @@ def test_mixed_batch_matches_zlib(engine):
     for i, s in enumerate(streams):
         buf[int(off[i]):int(off[i]) + len(s)] = np.frombuffer(s, dtype=np.uint8)
     lens = np.array([len(s) for s in streams], dtype=np.uint32)
-    out, out_len, status = engine.decompress_host(buf, lens, 40000, in_off=off, flags=3)
-    assert not status.any(), status
-    for i, d in enumerate(plains):
-        assert out[i, :out_len[i]].tobytes() == d, i
+    for route in (0, FORCE_LANES, FORCE_LANES | NO_LANE_SCRATCH):
+        out, out_len, status = engine.decompress_host(buf, lens, 40000, in_off=off, flags=3 | route)
+        assert not status.any(), (route, status)
+        for i, d in enumerate(plains):
+            assert out[i, :out_len[i]].tobytes() == d, (route, i)
 
 
 def test_multi_block_and_window(engine):
@@ -88,7 +89,7 @@ def test_multi_block_and_window(engine):
     assert engine.decompress(z, flags=3) == data
 
 
-FORCE_GENERAL, FORCE_LANES = 0x100, 0x200       # internal routing flags (csrc/hdlz_common.cuh)
+FORCE_GENERAL, FORCE_LANES, NO_LANE_SCRATCH = 0x100, 0x200, 0x400   # internal routing flags (csrc/hdlz_common.cuh)
 
 
 @pytest.mark.parametrize("route", [0, FORCE_GENERAL, FORCE_LANES])
@@ -108,7 +109,7 @@ def test_config3_zfixed_blocks(engine, route):
         assert out.tobytes() == b"".join(blocks)
 
 
-@pytest.mark.parametrize("route", [FORCE_GENERAL, FORCE_LANES])
+@pytest.mark.parametrize("route", [FORCE_GENERAL, FORCE_LANES, FORCE_LANES | NO_LANE_SCRATCH])
 def test_routes_agree_on_mixed_and_corrupt_streams(engine, route):
     """Fixed, stored, dynamic (handed over by the lane kernel), long-distance and corrupted streams:
     both routes must give zlib's bytes or an error status, never differ on valid streams."""
@@ -143,10 +144,11 @@ def test_routes_agree_on_mixed_and_corrupt_streams(engine, route):
             assert want is None or len(want) > 6000, (i, status[i])
 
 
-def test_config4_dynamic_32k(engine):
-    """BASELINE config 4 shape: 32 KiB plain, zlib level 6 dynamic trees, OBSIZE = 32768."""
+@pytest.mark.parametrize("route,n", [(0, 64), (FORCE_LANES, 64), (0, 1500)])
+def test_config4_dynamic_32k(engine, route, n):
+    """BASELINE config 4 shape: 32 KiB plain, zlib level 6 dynamic trees, OBSIZE = 32768; through the
+    warp-per-stream kernel (few streams) and the lane-per-stream kernel with per-lane tables (many)."""
     rnd = np.random.default_rng(4)
-    n = 64
     plains, streams = [], []
     for i in range(n):
         sym = rnd.zipf(1.3, 32768) % 64 + 32
@@ -161,7 +163,7 @@ def test_config4_dynamic_32k(engine):
     for i, s in enumerate(streams):
         buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
     lens = np.array([len(s) for s in streams], dtype=np.uint32)
-    out, out_len, status = engine.decompress_host(buf, lens, 32768, flags=3)
+    out, out_len, status = engine.decompress_host(buf, lens, 32768, flags=3 | route)
     assert not status.any() and (out_len == 32768).all()
     for i in range(n):
         assert out[i].tobytes() == plains[i]
