@@ -189,27 +189,24 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             // ---------------- phase A: byte-equality masks ----------------------------------------
             uint32_t s1 = 0, s2 = 0;
             {
-                // MATCH.ANY has ~100-150 cycles of latency under load (profiles/r01_ubench_*): keep the
-                // matches of the next two chunks in flight while the table steps of this one run
+                // The lane mask of the lanes holding the same byte is built with a shared-memory
+                // atomic OR into the table, not with MATCH.ANY: that instruction occupies the SM-wide
+                // ADU pipe for ~2 cycles per DISTINCT value among the 32 lanes (~40 cycles on this
+                // data, profiles/r01_ubench_match.txt) and made the whole kernel ADU-bound.
                 const int c0 = t0 > 0 ? -1 : 0;
-                uint32_t v1 = in_s[32 + 32 * c0 + lane];
-                uint32_t m1 = __match_any_sync(HDLZ_FULL_MASK, v1);
-                uint32_t v2 = in_s[32 + 32 * (c0 + 1) + lane];
-                uint32_t m2 = __match_any_sync(HDLZ_FULL_MASK, v2);
+                const uint32_t lane_bit = 1u << lane;
+                uint32_t vnext = in_s[32 + 32 * c0 + lane];
                 for (int c = c0; c <= kChunks; ++c) {
                     const int i = 32 * c + lane;                 // tile-relative position
-                    const uint32_t v = v1, mcur = m1;
-                    v1 = v2; m1 = m2;
-                    if (c + 2 <= kChunks) {
-                        v2 = in_s[32 + 32 * (c + 2) + lane];
-                        m2 = __match_any_sync(HDLZ_FULL_MASK, v2);
-                    }
+                    const uint32_t v = vnext;
+                    if (c < kChunks) vnext = in_s[32 + 32 * (c + 1) + lane];
                     const uint32_t mprev = T[v];
                     __syncwarp();
                     T[vprev] = 0;
                     __syncwarp();
-                    T[v] = mcur;
+                    atomicOr(&T[v], lane_bit);
                     __syncwarp();
+                    const uint32_t mcur = T[v];
                     vprev = v;
                     if (c >= 0) {
                         Rw[i + (i >> 5)] = __funnelshift_r(mprev, mcur, lane);   // bit k <=> distance 32 - k
