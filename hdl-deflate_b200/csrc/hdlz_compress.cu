@@ -39,6 +39,8 @@
 
 #include "hdlz_common.cuh"
 
+#include <type_traits>
+
 namespace hdlz {
 namespace {
 
@@ -68,7 +70,8 @@ static_assert(kOutWords <= kRWords, "the output stream part must fit in the toke
 constexpr int kLutWords = 256 + 36;   // LT[256] literal tokens, DC[33] distance part of match tokens
 constexpr size_t kSmemBytes = kLutWords * 4 + sizeof(WarpSmem) * kWarpsPerCta;
 
-// token word: bits 0..14 code (LSB-first), 16..19 bit count, 24..27 length in positions
+// token word: bits 0..14 code (LSB-first), 16..19 bit count, 24..29 = 4 * (length in positions - 1),
+// i.e. the nibble shift of the parse DP
 __device__ __forceinline__ uint32_t rev_n(uint32_t v, int n) { return __brev(v) >> (32 - n); }
 
 // distance part of a match token for distance d = cl + 1: (5-bit code + extra bits) << 7,
@@ -86,13 +89,13 @@ __device__ __forceinline__ uint32_t dist_token_entry(int cl)
         extra = e & ((1u << eb) - 1);
     }
     const uint32_t dc = rev_n(c, 5) | (extra << 5);
-    return (dc << 7) | ((12 + eb) << 16) | (3u << 24);
+    return (dc << 7) | ((12 + eb) << 16) | (8u << 24);
 }
 
 __device__ __forceinline__ uint32_t literal_token_entry(uint32_t x)
 {
     // fixed Huffman literal codes, bit-reversed (== out_codes[x], deflate.py:112-149); length 1
-    return (x < 144 ? (rev_n(0x30 + x, 8) | (8u << 16)) : (rev_n(0x100 + x, 9) | (9u << 16))) | (1u << 24);
+    return (x < 144 ? (rev_n(0x30 + x, 8) | (8u << 16)) : (rev_n(0x100 + x, 9) | (9u << 16)));
 }
 
 __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n)      // n >= 32 -> 0 (PTX shr semantics)
@@ -230,7 +233,9 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 #pragma unroll
                 for (int k = 0; k < 9; ++k) win[8 + k] = Rw[rbase + 33 + k];
                 __syncwarp();
-                for (int grp = 3; grp >= 0; --grp) {
+                // a token that starts at j reaches into the next segment only when j + 10 >= 32: the
+                // groups of the lower positions skip that case at compile time
+                auto group = [&](const int grp, auto can_exit) {
                     const int j0 = grp * 8;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) win[k] = Rw[rbase + j0 + k];
@@ -251,24 +256,31 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         }
                         const uint32_t n = (uint32_t)(sum >> ((31u - cl) & 31u));   // sum = n << (31 - cl)
                         const uint32_t x = ((k < 4 ? bv.x : bv.y) >> (8 * (k & 3))) & 255u;
-                        const uint32_t mt = (m3 ? DC[cl] : 0u) + (__brev(n + 1) >> 25) + (n << 24);
+                        const uint32_t mt = (m3 ? DC[cl] : 0u) + (__brev(n + 1) >> 25) + (n << 26);
                         const uint32_t lt = LT[x];
                         const uint32_t tk = m3 ? mt : lt;
                         tokv[k] = tk;
-                        const uint32_t ln = tk >> 24;
-                        const int ex = j + (int)ln - kSeg;
-                        const uint32_t look = (uint32_t)(H >> (4 * ln - 4)) & 15u;
-                        H = (H << 4) | (ex >= 0 ? (uint32_t)ex : look);
+                        const uint32_t ls = tk >> 24;                       // 4 * (length - 1)
+                        const uint32_t look = (uint32_t)(H >> ls) & 15u;
+                        if (decltype(can_exit)::value) {
+                            const int ex = j + 1 + (int)(ls >> 2) - kSeg;
+                            H = (H << 4) | (ex >= 0 ? (uint32_t)ex : look);
+                        } else {
+                            H = (H << 4) | look;
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) Rw[rbase + j0 + k] = tokv[k];
 #pragma unroll
                     for (int k = 8; k >= 0; --k) win[8 + k] = win[k];
-                }
+                };
+                group(3, std::true_type());
+                group(2, std::true_type());
+                for (int grp = 1; grp >= 0; --grp) group(grp, std::false_type());
             }
             __syncwarp();
             if (last_tile) {            // positions past the end of the stream emit nothing
-                for (int i = (int)n_tile + lane; i < kTile; i += 32) Rw[i + (i >> 5)] = 1u << 24;
+                for (int i = (int)n_tile + lane; i < kTile; i += 32) Rw[i + (i >> 5)] = 0;
                 __syncwarp();
             }
 
@@ -305,7 +317,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         const uint32_t tke = start ? tk : 0u;
                         acc |= (unsigned long long)(tke & 0x7FFFu) << fill;
                         fill += (tke >> 16) & 15u;
-                        r = (start ? (tk >> 24) : r) - 1;
+                        r = start ? (tk >> 26) : r - 1;
                     }
                     if (fill >= 32) {                        // fill < 32 + 2 * 15 < 64 between checks
                         priv[wcnt * 32 + lane] = (uint32_t)acc;
