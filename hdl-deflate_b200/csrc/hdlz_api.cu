@@ -146,6 +146,7 @@ int hdlz_destroy(hdlz_ctx *c)
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->d_off) cudaFree(c->d_off);
     if (c->d_work) cudaFree(c->d_work);
+    if (c->d_queue) cudaFree(c->d_queue);
     if (c->d_pack) cudaFree(c->d_pack);
     for (int i = 0; i < 3; i++)
         if (c->d_lane[i]) cudaFree(c->d_lane[i]);

@@ -98,10 +98,24 @@ __device__ __forceinline__ uint32_t literal_token_entry(uint32_t x)
     return (x < 144 ? (rev_n(0x30 + x, 8) | (8u << 16)) : (rev_n(0x100 + x, 9) | (9u << 16)));
 }
 
-__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n)      // n >= 32 -> 0 (PTX shr semantics)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)      // n >= 32 -> 0 (PTX shl semantics)
 {
     uint32_t r;
-    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long shr64_clamp(unsigned long long v, uint32_t n)   // n >= 64 -> 0
+{
+    unsigned long long r;
+    asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(n));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t find_msb(uint32_t v)                    // index of the highest set bit, 0xFFFFFFFF for 0
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
     return r;
 }
 
@@ -121,7 +135,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len,
            uint32_t uniform_len, uint8_t *__restrict__ out, uint64_t out_stride,
-           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams)
+           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue)
 {
     extern __shared__ uint4 smem_raw[];
     uint32_t *LT = reinterpret_cast<uint32_t *>(smem_raw);
@@ -131,7 +145,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
     WarpSmem &ws = reinterpret_cast<WarpSmem *>(LT + kLutWords)[warp];
 
     for (int i = threadIdx.x; i < 256; i += kWarpsPerCta * 32) LT[i] = literal_token_entry((uint32_t)i);
-    if (threadIdx.x < 36) DC[threadIdx.x] = threadIdx.x < 32 ? dist_token_entry(threadIdx.x) : 0u;
+    if (threadIdx.x < 36) DC[threadIdx.x] = threadIdx.x < 32 ? dist_token_entry(31 - (int)threadIdx.x) : 0u;   // by mask bit: d = 32 - f
     __syncthreads();
 
     uint8_t *in_s = ws.stage;                                  // byte i <-> position t0 - 32 + i
@@ -144,8 +158,13 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
     uint32_t vprev = 0;
     __syncwarp();
 
+    // Work distribution: every warp starts on stream <its global index>, later streams come from a
+    // device-wide queue head (one atomic per stream).  A static stride would leave the SM idle
+    // wherever a CTA of the grid was not resident from the start and ran after the others.
     const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
-    for (uint64_t sid = (uint64_t)blockIdx.x * kWarpsPerCta + warp; sid < n_streams; sid += n_warps) {
+    for (uint64_t sid = (uint64_t)blockIdx.x * kWarpsPerCta + warp; sid < n_streams;) {
+        unsigned long long next_ticket = 0;
+        if (lane == 0) next_ticket = atomicAdd(queue, 1ull);           // in flight while this stream is processed
         const uint32_t L = in_len ? in_len[sid] : uniform_len;
         const uint8_t *src = in + sid * in_stride;
         uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + sid * out_stride);
@@ -154,6 +173,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 out_len[sid] = 0;
                 if (status) status[sid] = L < HDLZ_MIN_INPUT ? HDLZ_ST_SHORT_INPUT : HDLZ_ST_OUT_OVERFLOW;
             }
+            sid = n_warps + __shfl_sync(HDLZ_FULL_MASK, next_ticket, 0);
             continue;
         }
 
@@ -245,8 +265,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     for (int k = 7; k >= 0; --k) {
                         const int j = j0 + k;
                         const uint32_t m3 = win[k] & win[k + 1] & win[k + 2];
-                        const uint32_t cl = __clz(m3);                      // 32 when there is no match
-                        uint32_t cbit = shr_clamp(0x80000000u, cl);
+                        const uint32_t f = find_msb(m3);                    // bit of the nearest distance, 0xFFFFFFFF: no match
+                        uint32_t cbit = shl_clamp(1u, f);
                         cbit &= win[k + 3];
                         unsigned long long sum = cbit;
 #pragma unroll
@@ -254,9 +274,9 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                             cbit &= win[k + e];
                             sum = add_wide(cbit, sum);
                         }
-                        const uint32_t n = (uint32_t)(sum >> ((31u - cl) & 31u));   // sum = n << (31 - cl)
+                        const uint32_t n = (uint32_t)shr64_clamp(sum, f);     // sum = n << f
                         const uint32_t x = ((k < 4 ? bv.x : bv.y) >> (8 * (k & 3))) & 255u;
-                        const uint32_t mt = (m3 ? DC[cl] : 0u) + (__brev(n + 1) >> 25) + (n << 26);
+                        const uint32_t mt = (m3 ? DC[f] : 0u) + (__brev(n + 1) >> 25) + (n << 26);
                         const uint32_t lt = LT[x];
                         const uint32_t tk = m3 ? mt : lt;
                         tokv[k] = tk;
@@ -400,6 +420,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
             }
         }
+        sid = n_warps + __shfl_sync(HDLZ_FULL_MASK, next_ticket, 0);
     }
 }
 
@@ -419,8 +440,12 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
     const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;      // persistent: a multiple of the SM count
     if (blocks > resident) blocks = resident;
+    // queue head of this launch: one of 16 slots, zeroed on the launch's own stream
+    if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, 16 * sizeof(unsigned long long)));
+    unsigned long long *queue = ctx->d_queue + (ctx->launches & 15);
+    HDLZ_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
     k_compress<<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len, d_out,
-                                                                        out_stride, d_out_len, d_status, n);
+                                                                        out_stride, d_out_len, d_status, n, queue);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;
