@@ -66,8 +66,11 @@ __constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65
                                       257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193,
                                       12289, 16385, 24577};
 
-// litlen entry: bits 0..3 code length, 4..7 extra bits, 8..9 kind (0 literal, 1 end of block,
-// 2 length, 3 invalid), 16.. value (byte or base length)
+// fixed litlen entry, indexed by 9 stream bits.
+//   literal     : bits 0..3 code length (8 | 9), bit 8 set, 16..23 the byte
+//   non-literal : bits 0..3 ZERO (so a literal-decode chain that meets one stops consuming: the
+//                 following look-ups see the same bits again), 4..7 code length, 9..10 kind
+//                 (1 end of block, 2 length, 3 invalid), 11..14 extra bits, 16.. base length
 __device__ uint32_t fixed_lit_entry(uint32_t idx9)
 {
     const uint32_t r9 = __brev(idx9) >> 23;          // the 9 bits MSB-first, as RFC 1951 3.2.6 lists codes
@@ -77,10 +80,10 @@ __device__ uint32_t fixed_lit_entry(uint32_t idx9)
     else if (c8 <= 0xBF) { sym = c8 - 0x30; nb = 8; }
     else if (c8 <= 0xC7) { sym = 280 + (c8 - 0xC0); nb = 8; }
     else { sym = 144 + (r9 - 0x190); nb = 9; }
-    if (sym < 256) return nb | (sym << 16);
-    if (sym == 256) return nb | (1u << 8);
-    if (sym > 285) return nb | (3u << 8);
-    return nb | ((uint32_t)c_lextra[sym - 257] << 4) | (2u << 8) | ((uint32_t)c_lbase[sym - 257] << 16);
+    if (sym < 256) return nb | 0x100u | (sym << 16);
+    if (sym == 256) return (nb << 4) | (1u << 9);
+    if (sym > 285) return (nb << 4) | (3u << 9);
+    return (nb << 4) | (2u << 9) | ((uint32_t)c_lextra[sym - 257] << 11) | ((uint32_t)c_lbase[sym - 257] << 16);
 }
 
 // distance entry (index = the 5 code bits as they sit in the stream): bits 0..3 extra bits,
@@ -177,6 +180,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     __shared__ uint32_t s_dist[32];       // fixed tree: 5 stream bits -> distance entry
     __shared__ uint32_t s_sym[288];       // literal/length symbol -> entry without code length
     __shared__ uint32_t s_dsym[32];       // distance symbol -> distance entry
+    __shared__ uint2 s_pat[8];            // min(distance, 4) -> {bytes of the source word to keep, replication factor}
     __shared__ uint32_t s_ring[kLWarps][kRing][32];
 
     for (int i = threadIdx.x; i < 512; i += kLWarps * 32) s_lit[i] = fixed_lit_entry((uint32_t)i);
@@ -184,6 +188,12 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     if (threadIdx.x < 32) {
         s_dist[threadIdx.x] = fixed_dist_entry(threadIdx.x);
         s_dsym[threadIdx.x] = fixed_dist_entry(__brev(threadIdx.x) >> 27);
+    }
+    if (threadIdx.x < 8) {
+        const uint32_t d = threadIdx.x;
+        s_pat[d] = d == 1 ? make_uint2(0xFFu, 0x01010101u) : d == 2 ? make_uint2(0xFFFFu, 0x00010001u)
+                   : d == 3 ? make_uint2(0xFFFFFFu, 0x01000001u) : d == 4 ? make_uint2(0xFFFFFFFFu, 1u)
+                                                                          : make_uint2(0u, 0u);
     }
     __syncthreads();
 
@@ -277,11 +287,10 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         }
         const uint32_t v = __funnelshift_r(w0, w1, 8u * (s & 3u));
         // distance < 4: the source overlaps what is being written -> period-`d` pattern:
-        // keep the first `d` bytes and replicate them with one multiply
-        const uint32_t dd = d < 4u ? d : 4u;
-        const uint32_t keep = 0xFFFFFFFFu >> ((32u - 8u * dd) & 31u);   // dd == 0 only on lanes that are not copying
-        const uint32_t mult = dd == 4u ? 1u : dd == 3u ? 0x01000001u : dd == 2u ? 0x00010001u : 0x01010101u;
-        return (v & keep) * mult;
+        // keep the first `d` bytes and replicate them with one multiply (factors from a small table;
+        // d == 0 only on lanes that are not copying)
+        const uint2 pat = s_pat[d < 4u ? d : 4u];
+        return (v & pat.x) * pat.y;
     };
     auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
 
@@ -344,23 +353,40 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             const uint32_t a32 = (uint32_t)acc;                      // >= 32 valid bits
             const uint32_t e0 = s_lit[a32 & 511u];
             {
-                bool go = decode;
-                uint32_t e = e0, x = a32;
+                // up to four literals.  No predicates in the chain: a non-literal entry has a zero in
+                // the consumed-bits field and a zero byte, so once one is met the remaining look-ups
+                // stay on it.  `tally` sums the entries' low fields: bits 0..5 consumed bits, 8..10
+                // number of literals.
+                uint32_t x = a32, e = e0, tally = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (k) e = s_lit[x & 511u];
-                    const uint32_t nb = e & 15u;
-                    go = go && (e & 0x300u) == 0 && used + nb <= 32u && nlit < room;
-                    lits |= go ? ((e >> 16) << (8 * k)) : 0u;
-                    used += go ? nb : 0u;
-                    nlit += go ? 1u : 0u;
-                    x >>= nb;                                        // only meaningful while go holds
+                    if (k == 3 && (tally & 63u) + (e & 15u) > 32u) e = 0;        // would run past the 32 valid bits
+                    lits = __byte_perm(lits, e, 0x3210 ^ ((0x6 ^ k) << (4 * k)));  // byte k of lits = byte 2 of e
+                    tally += e & 0x10Fu;
+                    x >>= e & 15u;
+                }
+                if (!decode) tally = 0;                              // the lane is in a copy: nothing is consumed
+                used = tally & 63u;
+                nlit = tally >> 8;
+                if (nlit > room) {
+                    // rare: the output ends inside this run of literals
+                    used = 0; nlit = 0; lits = 0;
+                    x = a32;
+                    while (nlit < room) {
+                        e = s_lit[x & 511u];
+                        if (!(e & 15u)) break;
+                        lits |= ((e >> 16) & 255u) << (8u * nlit);
+                        used += e & 15u;
+                        x >>= e & 15u;
+                        ++nlit;
+                    }
                 }
             }
             if (decode && nlit == 0) {
                 // first symbol is not a literal (or no room): <length code><extra><5-bit distance code><extra>,
                 // at most 8 + 5 + 5 + 13 = 31 bits, all inside the low word of the bit buffer
-                const uint32_t nb = e0 & 15u, eb = (e0 >> 4) & 15u, kind = (e0 >> 8) & 3u, base = e0 >> 16;
+                const uint32_t nb = (e0 >> 4) & 15u, eb = (e0 >> 11) & 15u, kind = (e0 >> 9) & 3u, base = e0 >> 16;
                 const uint32_t x1 = a32 >> nb;
                 const uint32_t len = base + (x1 & ((1u << eb) - 1u));
                 const uint32_t x2 = x1 >> eb;
@@ -369,10 +395,11 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 const uint32_t dnew = (de >> 8) + ((x2 >> 5) & ((1u << deb) - 1u));
                 if (kind == 2u) {
                     used = nb + eb + 5u + deb;
-                    if (deb == 15u) fail(HDLZ_ST_BAD_CODE);
-                    else if (dnew > o) fail(HDLZ_ST_DIST_TOO_FAR);         // "distance too big" (deflate.py:1506-1508)
-                    else if (len > room) fail(HDLZ_ST_OUT_OVERFLOW);
-                    else { rem = len; dist = dnew; }
+                    if (deb == 15u || dnew > o || len > room) {
+                        if (deb == 15u) fail(HDLZ_ST_BAD_CODE);
+                        else if (dnew > o) fail(HDLZ_ST_DIST_TOO_FAR);         // "distance too big" (deflate.py:1506-1508)
+                        else fail(HDLZ_ST_OUT_OVERFLOW);
+                    } else { rem = len; dist = dnew; }
                 } else if (kind == 1u) {
                     used = nb;
                     state = final_blk ? S_FINISH : S_HEADER;                // end of block
