@@ -213,7 +213,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     uint32_t state = S_IDLE;
 
     // per-stream state
-    uint32_t n_in = 0, nfull = 0;
+    uint32_t n_in = 0, nfull = 0, tailw = 0, nextw = 0;
     const uint8_t *src = in;
     uint8_t *dst = out;
     uint32_t *dst32 = reinterpret_cast<uint32_t *>(out);
@@ -227,17 +227,17 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     uint32_t rem = 0, dist = 1;      // bytes still to copy of the current match, its distance
     uint32_t trip = 0;
 
+    // input word w of the stream; the last, partial word was assembled once when the stream was opened
     auto load_word = [&](uint32_t w) -> uint32_t {
-        if (w < nfull) return __ldg(inw + w);
-        uint32_t v = 0;
-        if (w == nfull)
-            for (uint32_t b = 0; b < (n_in & 3u); ++b) v |= (uint32_t)src[4 * w + b] << (8 * b);
+        uint32_t v = w == nfull ? tailw : 0u;
+        if (w < nfull) v = __ldg(inw + w);
         return v;
     };
-    auto refill = [&]() {          // call when fill < 32
-        acc |= (uint64_t)load_word(wi) << fill;
+    auto refill = [&]() {          // call when fill < 32.  `nextw` is word `wi`, fetched one refill ahead
+        acc |= (uint64_t)nextw << fill;
         ++wi;
         fill += 32;
+        nextw = load_word(wi);
     };
     auto adler_bytes = [&](uint32_t v, uint32_t m) {
         for (uint32_t k = 0; k < m; ++k) {
@@ -332,7 +332,10 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         fail(HDLZ_ST_BAD_HEADER);
                 }
                 if (state == S_HEADER) {
+                    tailw = 0;
+                    for (uint32_t b = 0; b < (n_in & 3u); ++b) tailw |= (uint32_t)src[4 * nfull + b] << (8 * b);
                     acc = (uint64_t)(load_word(0) >> 16);      // skip the zlib header: di = 2 (deflate.py:644)
+                    nextw = load_word(1);
                     ring[0] = 0;
                 }
             }
