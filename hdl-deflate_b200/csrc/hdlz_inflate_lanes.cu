@@ -40,24 +40,15 @@ namespace {
 
 constexpr int kLWarps = 4;
 constexpr int kLaneCtasPerSm = 10;     // fixed/stored instantiation (48 registers)
-constexpr int kDynCtasPerSm = 1;       // dynamic-capable instantiation: the primary Huffman tables of its 128 lanes fill the shared memory
+constexpr int kDynCtasPerSm = 6;       // dynamic-capable instantiation (80 registers, 2.5 KiB of scratch per thread)
 constexpr int kRing = 32;   // words per lane (31 usable: the slot after the partial word is scratch)
 constexpr int kDynLitBits = 9;
 constexpr int kDynDistBits = 8;
 
 // per resident thread, global memory.  Table entry: (symbol << 4) | code length, 0 = longer code.
-// per resident thread, SHARED memory: the primary tables every symbol goes through.  The odd word
-// stride (385) keeps lock-step accesses of the 32 lanes to the same index on 32 different banks.
-struct LaneHot {
+struct LaneScratch {
     uint16_t lit[1 << kDynLitBits];
     uint16_t dist[1 << kDynDistBits];
-    uint32_t pad;
-};
-static_assert(sizeof(LaneHot) % 8 == 4, "LaneHot must be an odd number of words");
-constexpr size_t kDynSmemBytes = sizeof(LaneHot) * kLWarps * 32;
-
-// per resident thread, global memory: what only the table build and the rare long codes touch
-struct LaneScratch {
     uint16_t sorted_l[288];
     uint16_t sorted_d[32];
     uint16_t cnt_l[16];
@@ -216,8 +207,6 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     uint64_t sid = 0;
     uint32_t *ring = &s_ring[threadIdx.x >> 5][0][threadIdx.x & 31];     // word k at ring[k * 32]
     LaneScratch *my = (kDyn && scratch) ? scratch + gtid : nullptr;
-    extern __shared__ uint32_t s_hot_raw[];
-    LaneHot *hot = kDyn ? reinterpret_cast<LaneHot *>(s_hot_raw) + threadIdx.x : nullptr;
     bool to_dyn = false;            // hand this stream to the dynamic-capable instantiation
 
     const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) != 0;
@@ -432,7 +421,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             rem -= copying ? m : 0u;
             if (m && st == HDLZ_OK) append(copying ? sv : lits, m);
         } else if (kDyn && state == S_DYN) {
-            // ---- dynamic block: the same trip structure, primary tables in this lane's shared-memory slice ----
+            // ---- dynamic block: the same trip structure, tables in this lane's global scratch ----
             if (rem == 0) {
                 if (fill < 32) {
                     if (wi > nfull + 2) fail(HDLZ_ST_TRUNCATED);
@@ -445,7 +434,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     // up to four literals (or stop at the first other symbol)
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t x = (uint32_t)(acc >> used);
-                        e = hot->lit[x & ((1u << kDynLitBits) - 1u)];
+                        e = my->lit[x & ((1u << kDynLitBits) - 1u)];
                         if ((e & 15u) == 0) e = lane_slow_decode(x, my->cnt_l, my->sorted_l);
                         const uint32_t nb = e & 15u;
                         if (nb == 0 || (e >> 4) >= 256u || used + nb > 32u || nlit >= room) break;
@@ -477,7 +466,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                             acc >>= nb + eb; fill -= nb + eb;
                             if (fill < 32) refill();
                             const uint32_t y = (uint32_t)acc;
-                            uint32_t d = hot->dist[y & ((1u << kDynDistBits) - 1u)];
+                            uint32_t d = my->dist[y & ((1u << kDynDistBits) - 1u)];
                             if ((d & 15u) == 0) d = lane_slow_decode(y, my->cnt_d, my->sorted_d);
                             const uint32_t dnb = d & 15u;
                             const uint32_t de = s_dsym[(d >> 4) & 31u];
@@ -541,7 +530,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 for (int i = 0; i < 19; ++i) lens[i] = 0;
                 for (uint32_t i = 0; i < ncode; ++i) lens[c_clorder[i]] = (uint8_t)get(3);
                 // code-length code: 7-bit table in the (not yet built) distance table area
-                if (!bad) bad = lane_build(lens, 19, hot->dist, 7, my->cnt_d, my->sorted_d, false);
+                if (!bad) bad = lane_build(lens, 19, my->dist, 7, my->cnt_d, my->sorted_d, false);
                 if (!bad) {
                     uint32_t any = 0;
                     for (int l = 1; l <= 7; ++l) any |= my->cnt_d[l];
@@ -556,7 +545,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         if (wi > nfull + 2) { bad = 2; break; }
                         refill();
                     }
-                    const uint32_t e = hot->dist[(uint32_t)acc & 127u];
+                    const uint32_t e = my->dist[(uint32_t)acc & 127u];
                     const uint32_t nb = e & 15u, sym = e >> 4;
                     if (nb == 0) { bad = 1; break; }
                     acc >>= nb; fill -= nb;
@@ -572,8 +561,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     idx += rep;
                 }
                 if (!bad && ll[256] == 0) bad = 1;                           // no end-of-block code
-                if (!bad) bad = lane_build(ll + nlen, (int)ndist, hot->dist, kDynDistBits, my->cnt_d, my->sorted_d, true);
-                if (!bad) bad = lane_build(ll, (int)nlen, hot->lit, kDynLitBits, my->cnt_l, my->sorted_l, true);
+                if (!bad) bad = lane_build(ll + nlen, (int)ndist, my->dist, kDynDistBits, my->cnt_d, my->sorted_d, true);
+                if (!bad) bad = lane_build(ll, (int)nlen, my->lit, kDynLitBits, my->cnt_l, my->sorted_l, true);
                 if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
                 else state = S_DYN;
             }
@@ -663,13 +652,7 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     if (scratch) {
-        static bool attr_set[64] = {false};
-        if (!attr_set[ctx->device & 63]) {
-            HDLZ_CUDA(cudaFuncSetAttribute(k_inflate_lanes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kDynSmemBytes));
-            attr_set[ctx->device & 63] = true;
-        }
-        k_inflate_lanes<true><<<(unsigned)dyn_blocks, kLWarps * 32, kDynSmemBytes, s>>>(
+        k_inflate_lanes<true><<<(unsigned)dyn_blocks, kLWarps * 32, 0, s>>>(
             d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n, flags, list, count,
             nullptr, nullptr, dyn_list, dyn_count, scratch);
         ctx->launches++;
