@@ -101,6 +101,16 @@ class Engine(object):
     def launch_count(self):
         return int(self._lib.hdlz_launch_count(self._ctx))
 
+    @property
+    def match10(self):
+        """The reference's MATCH10 switch (deflate.py:34-35): True = matches up to 10 bytes (default),
+        False = up to 5."""
+        return bool(self._lib.hdlz_get_match10(self._ctx))
+
+    @match10.setter
+    def match10(self, on):
+        self._check(self._lib.hdlz_set_match10(self._ctx, 1 if on else 0))
+
     # ---- one stream: a STARTC / STARTD job ---------------------------------------------
     def compress(self, data):
         """zlib stream of `data`, bit-identical to the reference's FAST+MATCH10 output."""

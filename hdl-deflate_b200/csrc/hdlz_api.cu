@@ -122,6 +122,7 @@ int hdlz_create(int device, hdlz_ctx **out)
     memset(c, 0, sizeof *c);
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->max_match = HDLZ_MAX_MATCH;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -156,6 +157,15 @@ int hdlz_destroy(hdlz_ctx *c)
 }
 
 uint32_t hdlz_compress_bound(uint32_t len) { return compress_bound(len); }
+
+int hdlz_set_match10(hdlz_ctx *ctx, int match10)
+{
+    if (!ctx) return set_error(HDLZ_ERR_INVALID, "null context");
+    ctx->max_match = match10 ? HDLZ_MAX_MATCH : HDLZ_MAX_MATCH_SHORT;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_get_match10(hdlz_ctx *ctx) { return ctx && ctx->max_match == HDLZ_MAX_MATCH ? 1 : 0; }
 
 int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                         uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,

@@ -16,6 +16,7 @@
 struct hdlz_ctx {
     int device;
     int sm_count;
+    uint32_t max_match;  // longest match of the compressor: 10 (MATCH10, default) or 5 (deflate.py:34-35)
     // scratch for the host-buffer entry points (grown on demand, reused)
     uint8_t *d_in;
     size_t d_in_cap;

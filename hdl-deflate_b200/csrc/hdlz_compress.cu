@@ -132,6 +132,8 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 
+// kMaxMatch: 10 = the reference's MATCH10 configuration, 5 = MATCH10 False (deflate.py:34-35, 913-924)
+template <int kMaxMatch>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len,
            uint32_t uniform_len, uint8_t *__restrict__ out, uint64_t out_stride,
@@ -270,7 +272,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         cbit &= win[k + 3];
                         unsigned long long sum = cbit;
 #pragma unroll
-                        for (int e = 4; e < 10; ++e) {
+                        for (int e = 4; e < kMaxMatch; ++e) {
                             cbit &= win[k + e];
                             sum = add_wide(cbit, sum);
                         }
@@ -433,8 +435,10 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     static bool attr_set[64] = {false};
     if (n == 0) return HDLZ_SUCCESS;
     if (!attr_set[ctx->device & 63]) {
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[ctx->device & 63] = true;
     }
     uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -444,8 +448,12 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, 16 * sizeof(unsigned long long)));
     unsigned long long *queue = ctx->d_queue + (ctx->launches & 15);
     HDLZ_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
-    k_compress<<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len, d_out,
-                                                                        out_stride, d_out_len, d_status, n, queue);
+    if (ctx->max_match == 5)
+        k_compress<5><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
+                                                                               d_out, out_stride, d_out_len, d_status, n, queue);
+    else
+        k_compress<10><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
+                                                                                d_out, out_stride, d_out_len, d_status, n, queue);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;

@@ -27,7 +27,9 @@ from myhdl import always, block, Error
 
 IDLE, WRITE, READ, STARTC, STARTD = range(5)
 
-# feature flags of the reference (deflate.py:20-41): the configuration this engine implements
+# feature flags of the reference (deflate.py:20-41): the configuration this engine implements.
+# MATCH10 may be set to False before a block is instantiated (as with the reference, where it is a
+# module global read at elaboration): the engine then stops matches at 5 bytes (deflate.py:913-924).
 LOWLUT = False
 COMPRESS = True
 DECOMPRESS = True
@@ -83,12 +85,15 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
     ring = bytearray(IBSIZE)       # mirror of iram: what a byte address holds if never rewritten
     lin = bytearray()              # bytes by full address since the last write at address 0
     st = {"isize": 0, "job": IDLE, "out": b""}
+    match10 = bool(MATCH10)        # read at elaboration, like every configuration global of the reference
 
     def run_job():
         data = bytes(lin[:st["isize"] + 1])
         eng = _get_backend()
         try:
             if st["job"] == STARTC:
+                if hasattr(eng, "match10"):
+                    eng.match10 = match10
                 return eng.compress(data)
             return eng.decompress(data)
         except ValueError as e:            # StreamError: non-zero hdlz_status

@@ -40,6 +40,7 @@ extern "C" {
 /* Engine constants the reference exports as module globals (deflate.py:56-89). */
 #define HDLZ_CWINDOW 32      /* search window, FAST (deflate.py:56-57)               */
 #define HDLZ_MAX_MATCH 10    /* MATCH10 (deflate.py:34-35, 913-952)                  */
+#define HDLZ_MAX_MATCH_SHORT 5 /* MATCH10 = False: SEARCHF stops at 5 (deflate.py:913-924) */
 #define HDLZ_MIN_INPUT 5     /* engine idles while isize < 4 (deflate.py:429-432)    */
 #define HDLZ_OBSIZE 32768    /* decompress window, "ALL valid streams" (README:20-21) */
 #define HDLZ_LMAX 24         /* width of progress / address counters (deflate.py:73-76) */
@@ -88,6 +89,13 @@ int hdlz_destroy(hdlz_ctx *ctx);
 /* Worst-case compressed size of `len` input bytes: 2 + ceil((3 + 9*len + 7)/8) + 4,
  * rounded up to 16 (all-9-bit literals; CSTATIC framing deflate.py:746-814). */
 uint32_t hdlz_compress_bound(uint32_t len);
+
+/* The reference's module switch MATCH10 (deflate.py:34-35): non-zero (the default, and what the
+ * BASELINE configs use) lets SEARCHF grow a match to 10 bytes, zero stops it at 5 (deflate.py:913-924).
+ * Applies to every later compress call of the context; output is bit-identical to deflate.py built
+ * with the same setting (FAST = True, CWINDOW = 32). */
+int hdlz_set_match10(hdlz_ctx *ctx, int match10);
+int hdlz_get_match10(hdlz_ctx *ctx);
 
 /* ---- compress: STARTC job (deflate.py:618-633; CSTATIC/SEARCH/SEARCHF/DISTANCE/CHECKSUM :734-1016) ----
  * Block i = d_in[i*in_stride .. +len_i), len_i = d_in_len ? d_in_len[i] : uniform_len

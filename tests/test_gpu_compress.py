@@ -31,6 +31,31 @@ def test_golden_vectors_bit_exact(engine):
         assert hashlib.sha256(got).hexdigest() == c["out_sha256"], c["name"]
 
 
+def test_match10_false_bit_exact(engine):
+    """The reference's MATCH10 = False configuration (matches of 3..5 bytes, deflate.py:34-35,
+    913-924): fixtures produced by the executing reference, then a batch against the oracle."""
+    assert engine.match10
+    engine.match10 = False
+    try:
+        assert not engine.match10
+        for c in load_golden("compress_golden_match5.json"):
+            got = engine.compress(golden_input(c))
+            assert len(got) == c["out_len"], c["name"]
+            assert hashlib.sha256(got).hexdigest() == c["out_sha256"], c["name"]
+        n = 2048
+        arr = np.frombuffer(b"".join(workload.blocks(9000, n, 2048)), dtype=np.uint8).reshape(n, 2048)
+        out, out_len, status = engine.compress_host(arr)
+        assert not status.any()
+        for i in range(n):
+            st, want = hdlz_oracle.compress(arr[i].tobytes(), maxlen=5)
+            assert st == 0 and out[i, :out_len[i]].tobytes() == want, i
+        back, back_len, bst = engine.decompress_host(out, out_len, 2048)
+        assert not bst.any() and np.array_equal(back, arr)
+    finally:
+        engine.match10 = True
+    assert engine.compress(b"a" * 12).hex() == "789c4b8483c444001d9a048d"
+
+
 def test_batch_matches_oracle(engine):
     n = 8192
     arr = np.frombuffer(b"".join(workload.blocks(5000, n, 2048)), dtype=np.uint8).reshape(n, 2048)

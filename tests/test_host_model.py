@@ -79,6 +79,26 @@ def test_preload_flow_and_read_latency():
     assert back == data
 
 
+def test_match10_switch_is_read_at_elaboration():
+    """MATCH10 is a module global of the reference (deflate.py:34-35) read when the block is built."""
+    from port_driver import import_dropin
+    _, m = import_dropin()
+    data = " ".join("   Hello World! %d     " % i for i in range(100)).encode()[:1000]
+    m.MATCH10 = False
+    try:
+        p = Port(OracleEngine())
+        p.pulse_reset()
+        comp5 = p.preload(p.m.STARTC, data)
+    finally:
+        m.MATCH10 = True
+    p = Port(OracleEngine())
+    p.pulse_reset()
+    comp10 = p.preload(p.m.STARTC, data)
+    assert comp5 == hdlz_oracle.compress(data, maxlen=5)[1]
+    assert comp10 == hdlz_oracle.compress(data)[1]
+    assert comp5 != comp10 and zlib.decompress(comp5) == data
+
+
 def test_start_ignored_while_busy_and_below_four_bytes():
     p = Port(OracleEngine())
     m = p.m

@@ -24,6 +24,22 @@ def test_compress_restatement_matches_golden():
         assert zlib.decompress(out) == data          # the reference's own check (test_deflate.py:285)
 
 
+def test_compress_restatement_matches_golden_match5():
+    """MATCH10 = False (deflate.py:34-35, 913-924): fixtures of oracle/make_golden_match5.py."""
+    cases = load_golden("compress_golden_match5.json")
+    assert len(cases) >= 60
+    differs = 0
+    for c in cases:
+        data = golden_input(c)
+        st, out = hdlz_oracle.compress(data, maxlen=5)
+        assert st == 0
+        assert len(out) == c["out_len"], c["name"]
+        assert hashlib.sha256(out).hexdigest() == c["out_sha256"], c["name"]
+        assert zlib.decompress(out) == data
+        differs += out != hdlz_oracle.compress(data)[1]
+    assert differs > 10            # the switch changes the streams
+
+
 def test_survey_known_answers():
     # SURVEY.md 8(a): vectors produced by the reference FSM
     assert hdlz_oracle.compress(b"abcde")[1].hex() == "789c4b4c4a4e49050005c801f0"
