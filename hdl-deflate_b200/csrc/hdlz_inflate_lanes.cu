@@ -181,6 +181,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     __shared__ uint32_t s_sym[288];       // literal/length symbol -> entry without code length
     __shared__ uint32_t s_dsym[32];       // distance symbol -> distance entry
     __shared__ uint2 s_pat[8];            // min(distance, 4) -> {bytes of the source word to keep, replication factor}
+    __shared__ unsigned long long s_mask8[9];   // n -> mask of the low n bytes
+    __shared__ unsigned long long s_mult8[9];   // min(distance, 8) -> factor that repeats the low `distance` bytes over 8
     __shared__ uint32_t s_ring[kLWarps][kRing][32];
 
     for (int i = threadIdx.x; i < 512; i += kLWarps * 32) s_lit[i] = fixed_lit_entry((uint32_t)i);
@@ -188,6 +190,13 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     if (threadIdx.x < 32) {
         s_dist[threadIdx.x] = fixed_dist_entry(threadIdx.x);
         s_dsym[threadIdx.x] = fixed_dist_entry(__brev(threadIdx.x) >> 27);
+    }
+    if (threadIdx.x < 9) {
+        const uint32_t d = threadIdx.x;
+        s_mask8[d] = d == 0 ? 0ull : d == 8 ? ~0ull : (1ull << (8 * d)) - 1ull;
+        unsigned long long mul = 0;
+        for (uint32_t sh = 0; d && sh < 64; sh += 8 * d) mul |= 1ull << sh;
+        s_mult8[d] = mul;
     }
     if (threadIdx.x < 8) {
         const uint32_t d = threadIdx.x;
@@ -278,7 +287,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         const uint32_t s = o - d;
         const uint32_t ws = s >> 2, wo = o >> 2;
         uint32_t w0, w1;
-        if (wo - ws < (uint32_t)(kRing - 1)) {
+        if (wo - ws < (uint32_t)(kRing - 2)) {          // the eight-byte append uses two slots past the partial word
             w0 = ring[(ws & (kRing - 1)) * 32];
             w1 = ring[((ws + 1u) & (kRing - 1)) * 32];
         } else {
@@ -292,10 +301,50 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         const uint2 pat = s_pat[d < 4u ? d : 4u];
         return (v & pat.x) * pat.y;
     };
+    // eight-byte forms for the fixed-block trip: bytes s .. s+7 of the output (s = o - d) ...
+    auto source8 = [&](uint32_t d) -> unsigned long long {
+        const uint32_t s = o - d;
+        const uint32_t ws = s >> 2, wo = o >> 2;
+        uint32_t w0, w1, w2;
+        if (wo - ws < (uint32_t)(kRing - 2)) {
+            w0 = ring[(ws & (kRing - 1)) * 32];
+            w1 = ring[((ws + 1u) & (kRing - 1)) * 32];
+            w2 = ring[((ws + 2u) & (kRing - 1)) * 32];
+        } else {
+            w0 = dst32[ws];
+            w1 = dst32[ws + 1u];
+            w2 = dst32[ws + 2u];
+        }
+        const uint32_t sh = 8u * (s & 3u);
+        const unsigned long long v = (unsigned long long)__funnelshift_r(w0, w1, sh) |
+                                     ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+        // distance < 8: keep the first `d` bytes and repeat them (d == 0 only on lanes that are not copying)
+        const uint32_t dd = d < 8u ? d : 8u;
+        return (v & s_mask8[dd]) * s_mult8[dd];
+    };
+    // ... and appending the low m (1..8) bytes of v: three ring words are written back
+    auto append8 = [&](unsigned long long v, uint32_t m) {
+        v &= s_mask8[m];
+        if (want_adler) {
+            adler_bytes((uint32_t)v, m < 4u ? m : 4u);
+            if (m > 4u) adler_bytes((uint32_t)(v >> 32), m - 4u);
+        }
+        const uint32_t ob = o & 3u, wo = o >> 2, sh = 8u * ob;
+        const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        const uint32_t wa = cw | (lo << sh);
+        const uint32_t wb = __funnelshift_l(lo, hi, sh);
+        const uint32_t wc = __funnelshift_l(hi, 0u, sh);
+        o += m;
+        ring[(wo & (kRing - 1)) * 32] = wa;
+        ring[((wo + 1u) & (kRing - 1)) * 32] = wb;
+        ring[((wo + 2u) & (kRing - 1)) * 32] = wc;
+        const uint32_t nw = (ob + m) >> 2;
+        cw = nw == 0u ? wa : nw == 1u ? wb : wc;
+    };
     auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
 
     while (__any_sync(HDLZ_FULL_MASK, state != S_DONE)) {
-        // every 8 trips (a trip appends at most 4 bytes, so at most 8 words accumulate) all lanes
+        // every 8 trips (a trip appends at most 8 bytes, so at most 16 words accumulate on top of 7) all lanes
         // store their completed 32-byte groups together
         if ((++trip & 7u) == 0) flush8();
 
@@ -343,7 +392,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         }
 
         if (state == S_FIXED) {
-            // ---- fixed block (NEXT / INFLATE / COPY): every trip appends at most four bytes ----
+            // ---- fixed block (NEXT / INFLATE / COPY): every trip appends at most eight bytes ----
             // A lane either continues the copy it is in (rem != 0) or decodes: up to four
             // consecutive literals (packed into one append), or one match / end-of-block code.
             if (fill < 32) {
@@ -414,12 +463,12 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 }
             }
             acc >>= used; fill -= used;
-            // one append step: the literals, or up to four bytes of the copy (COPY, deflate.py:1627-1656)
+            // one append step: the literals, or up to eight bytes of the copy (COPY, deflate.py:1627-1656)
             const bool copying = rem != 0;
-            const uint32_t sv = source(copying ? dist : 0u);
-            const uint32_t m = copying ? (rem < 4u ? rem : 4u) : nlit;
+            const unsigned long long sv = source8(copying ? dist : 0u);
+            const uint32_t m = copying ? (rem < 8u ? rem : 8u) : nlit;
             rem -= copying ? m : 0u;
-            if (m && st == HDLZ_OK) append(copying ? sv : lits, m);
+            if (m && st == HDLZ_OK) append8(copying ? sv : (unsigned long long)lits, m);
         } else if (kDyn && state == S_DYN) {
             // ---- dynamic block: the same trip structure, tables in this lane's global scratch ----
             if (rem == 0) {
