@@ -350,7 +350,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
         // ---- when every lane of the warp is between streams, all take their next stream together
         // (a per-lane refetch would run this and the block header with one or two active lanes)
-        if (__all_sync(HDLZ_FULL_MASK, state == S_IDLE || state == S_DONE)) {
+        // (looked at every eighth trip: the vote is not free and a finished lane can wait that long)
+        if ((trip & 7u) == 1u && __all_sync(HDLZ_FULL_MASK, state == S_IDLE || state == S_DONE)) {
             if (state == S_IDLE) {
             if (next_item >= n_items) {
                 state = S_DONE;
@@ -395,10 +396,9 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             // ---- fixed block (NEXT / INFLATE / COPY): every trip appends at most eight bytes ----
             // A lane either continues the copy it is in (rem != 0) or decodes: up to four
             // consecutive literals (packed into one append), or one match / end-of-block code.
-            if (fill < 32) {
-                if (wi > nfull + 2) fail(HDLZ_ST_TRUNCATED);
-                else refill();
-            }
+            // Past the end of the input the bit buffer is fed zeros, which the fixed tree reads as
+            // end-of-block: a truncated stream reaches S_FINISH / S_HEADER, where the position is checked.
+            if (fill < 32) refill();
             const bool decode = state == S_FIXED && rem == 0;
             const uint32_t room = out_cap - o;                       // o <= out_cap always
             uint32_t used = 0, lits = 0, nlit = 0;
@@ -539,10 +539,13 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             }
         } else if (state == S_HEADER) {
             if (fill < 32) refill();
+            const bool past_end = (uint64_t)wi * 32 - fill + 3 > 8ull * n_in;
             final_blk = (uint32_t)acc & 1u;
-            const uint32_t type = ((uint32_t)acc >> 1) & 3u;
+            const uint32_t type = past_end ? 4u : ((uint32_t)acc >> 1) & 3u;
             acc >>= 3; fill -= 3;
-            if (type == 1) {
+            if (type == 4) {
+                fail(HDLZ_ST_TRUNCATED);                                    // "NO EOF!" (deflate.py:1535-1539)
+            } else if (type == 1) {
                 state = S_FIXED;
             } else if (type == 3) {
                 fail(HDLZ_ST_BAD_BTYPE);                                    // "Bad method" (deflate.py:718-721)
