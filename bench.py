@@ -416,9 +416,9 @@ def main():
         ns = min(args.ref_blocks, n)
         sample = d_in.view(n, BLOCK)[:ns].cpu().numpy()
         v, c, d, secs = cpu_roundtrip(sample, cores)
-        rep = max(1, int(12.0 / max(secs, 1e-3)))
+        rep = max(1, int(20.0 / max(secs, 1e-3)))
         if rep > 1:
-            v, c, d, secs = cpu_roundtrip(sample, cores, repeat=min(rep, 64))
+            v, c, d, secs = cpu_roundtrip(sample, cores, repeat=min(rep, 128))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "first %d blocks of the workload, %.1f s of CPU work, %d threads"
                                           % (ns, secs, cores),
