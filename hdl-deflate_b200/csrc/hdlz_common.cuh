@@ -32,7 +32,8 @@ struct hdlz_ctx {
     size_t d_lane_cap[3];
     uint64_t *h_small;  // pinned: per-chunk packed sizes
     size_t h_small_cap;
-    unsigned long long *d_queue;  // 16 work-queue heads of the persistent compress grid (one per launch in flight)
+    unsigned long long *d_queue;  // work-queue heads of the persistent compress grid, one slot per launch (ring)
+    unsigned queue_seq;
     uint32_t *d_work;  // [0] count, [4..] stream ids handed from the lane kernel to the warp kernel
     size_t d_work_cap;
     cudaStream_t stream;  // owned, used by the host-buffer entry points

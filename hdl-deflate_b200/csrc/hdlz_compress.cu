@@ -444,9 +444,12 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
     const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;      // persistent: a multiple of the SM count
     if (blocks > resident) blocks = resident;
-    // queue head of this launch: one of 16 slots, zeroed on the launch's own stream
-    if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, 16 * sizeof(unsigned long long)));
-    unsigned long long *queue = ctx->d_queue + (ctx->launches & 15);
+    // queue head of this launch: the next of kQueueSlots slots, zeroed on the launch's own stream.  A slot
+    // comes round again after kQueueSlots compress launches of this context, far more than can be in
+    // flight on its streams at once.
+    constexpr unsigned kQueueSlots = 4096;
+    if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, kQueueSlots * sizeof(unsigned long long)));
+    unsigned long long *queue = ctx->d_queue + (ctx->queue_seq++ & (kQueueSlots - 1));
     HDLZ_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
     if (ctx->max_match == 5)
         k_compress<5><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
