@@ -26,10 +26,13 @@ LMAX = 24
 MIN_INPUT = 5
 
 F_VERIFY_HEADER = 1
-F_VERIFY_ADLER = 2
+F_VERIFY_ADLER = 2     # the container checksum: Adler-32 (zlib) or CRC-32 + ISIZE (gzip)
+F_RAW = 4              # decompress: bare RFC 1951 stream
+F_GZIP = 8             # decompress: one RFC 1952 member
+CONTAINER_ZLIB, CONTAINER_RAW, CONTAINER_GZIP = 0, 1, 2
 
 STATUS_NAMES = ("OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR", "TRUNCATED",
-                "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER")
+                "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER", "BAD_CRC")
 
 # the message the reference raises for the condition (deflate.py:721, 1140, 1508, 1539, 1560)
 REFERENCE_MESSAGES = {
@@ -58,8 +61,8 @@ class StreamError(ValueError):
         ValueError.__init__(self, "%s (%s)" % (REFERENCE_MESSAGES.get(self.status, "error"), name))
 
 
-def compress_bound(n):
-    return int(_native.load().hdlz_compress_bound(int(n)))
+def compress_bound(n, container=CONTAINER_ZLIB):
+    return int(_native.load().hdlz_compress_bound_ex(int(n), int(container)))
 
 
 def _ptr(a):
@@ -111,12 +114,22 @@ class Engine(object):
     def match10(self, on):
         self._check(self._lib.hdlz_set_match10(self._ctx, 1 if on else 0))
 
+    @property
+    def container(self):
+        """Framing the compressor writes around the deflate body: CONTAINER_ZLIB (the reference's,
+        default), CONTAINER_RAW or CONTAINER_GZIP."""
+        return int(self._lib.hdlz_get_container(self._ctx))
+
+    @container.setter
+    def container(self, kind):
+        self._check(self._lib.hdlz_set_container(self._ctx, int(kind)))
+
     # ---- one stream: a STARTC / STARTD job ---------------------------------------------
     def compress(self, data):
         """zlib stream of `data`, bit-identical to the reference's FAST+MATCH10 output."""
         data = bytes(data)
         src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
-        cap = compress_bound(len(data))
+        cap = compress_bound(len(data), self.container)
         out = np.empty(cap, dtype=np.uint8)
         n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
         self._check(self._lib.hdlz_compress_stream(self._ctx, src.ctypes.data, len(data), out.ctypes.data, cap,
@@ -154,7 +167,7 @@ class Engine(object):
         else:
             maxlen = in_stride
         if out_stride is None:
-            out_stride = compress_bound(maxlen)
+            out_stride = compress_bound(maxlen, self.container)
         out = np.empty((n, out_stride), dtype=np.uint8)
         out_len = np.zeros(n, dtype=np.uint32)
         status = np.zeros(n, dtype=np.uint32)
@@ -172,7 +185,7 @@ class Engine(object):
             maxlen = int(lens.max()) if n else 0
         else:
             maxlen = in_stride
-        cap = n * compress_bound(maxlen)
+        cap = n * compress_bound(maxlen, self.container)
         out = np.empty(max(cap, 16), dtype=np.uint8)
         off = np.zeros(n, dtype=np.uint64)
         out_len = np.zeros(n, dtype=np.uint32)

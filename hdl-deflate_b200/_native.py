@@ -22,6 +22,9 @@ SIGNATURES = {
     "hdlz_compress_bound": (u32, [u32]),
     "hdlz_set_match10": (cint, [vp, cint]),
     "hdlz_get_match10": (cint, [vp]),
+    "hdlz_set_container": (cint, [vp, cint]),
+    "hdlz_get_container": (cint, [vp]),
+    "hdlz_compress_bound_ex": (u32, [u32, cint]),
     "hdlz_compress_batch": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u32p, c_u32p, u64, vp]),
     "hdlz_decompress_batch": (cint, [vp, c_u8p, c_u64p, u64, c_u32p, c_u8p, u64, u32, c_u32p, c_u32p, u64, u32, vp]),
     "hdlz_compress_host": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u32p, c_u32p, u64]),

@@ -88,7 +88,8 @@ const char *hdlz_last_error(void) { return g_err; }
 const char *hdlz_status_name(uint32_t s)
 {
     static const char *names[] = {"OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR",
-                                  "TRUNCATED", "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER"};
+                                  "TRUNCATED", "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER",
+                                  "BAD_CRC"};
     return s < sizeof(names) / sizeof(names[0]) ? names[s] : "UNKNOWN";
 }
 
@@ -166,6 +167,19 @@ int hdlz_set_match10(hdlz_ctx *ctx, int match10)
 }
 
 int hdlz_get_match10(hdlz_ctx *ctx) { return ctx && ctx->max_match == HDLZ_MAX_MATCH ? 1 : 0; }
+
+int hdlz_set_container(hdlz_ctx *ctx, int container)
+{
+    if (!ctx) return set_error(HDLZ_ERR_INVALID, "null context");
+    if (container < HDLZ_CONTAINER_ZLIB || container > HDLZ_CONTAINER_GZIP)
+        return set_error(HDLZ_ERR_INVALID, "unknown container %d", container);
+    ctx->container = (uint32_t)container;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_get_container(hdlz_ctx *ctx) { return ctx ? (int)ctx->container : 0; }
+
+uint32_t hdlz_compress_bound_ex(uint32_t len, int container) { return compress_bound(len, (uint32_t)container); }
 
 int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                         uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
@@ -329,7 +343,7 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
         maxlen = 0;
         for (uint64_t i = 0; i < n; i++) maxlen = in_len[i] > maxlen ? in_len[i] : maxlen;
     }
-    const uint64_t slot = compress_bound(maxlen);
+    const uint64_t slot = compress_bound(maxlen, ctx->container);
     const uint64_t chunk = host_chunk(n, in_stride + slot);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, (size_t)n * in_stride))) return rc;
@@ -402,7 +416,7 @@ int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t
     if (len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
     *out_len = 0;
     const size_t in_slot = ((size_t)len + 15) & ~(size_t)15;
-    const size_t out_slot = compress_bound(len);
+    const size_t out_slot = compress_bound(len, ctx->container);
     if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, in_slot + 16))) return rc;
     if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_slot))) return rc;
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * sizeof(uint32_t)))) return rc;

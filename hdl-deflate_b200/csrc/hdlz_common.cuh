@@ -16,6 +16,7 @@
 struct hdlz_ctx {
     int device;
     int sm_count;
+    uint32_t container;  // hdlz_container written by the compressor
     uint32_t max_match;  // longest match of the compressor: 10 (MATCH10, default) or 5 (deflate.py:34-35)
     // scratch for the host-buffer entry points (grown on demand, reused)
     uint8_t *d_in;
@@ -65,13 +66,17 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
 inline size_t inflate_work_words(uint64_t n) { return 2 * (size_t)n + 16; }
 int launch_pack(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
                 uint64_t *d_off, uint64_t *d_total, uint64_t n, cudaStream_t s);
+int launch_gzip_trailers(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                         uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, const uint32_t *d_out_len,
+                         uint64_t n, cudaStream_t s);
 int launch_generate(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,
                     uint64_t first_block, cudaStream_t s);
 
-__host__ __device__ inline uint32_t compress_bound(uint32_t len)
+__host__ __device__ inline uint32_t compress_bound(uint32_t len, uint32_t container = HDLZ_CONTAINER_ZLIB)
 {
-    // 2 header + ceil((3 + 9*len + 7) / 8) + 4 Adler, rounded up to 16
-    uint64_t b = 2ull + (3ull + 9ull * len + 7ull + 7ull) / 8ull + 4ull;
+    // header + ceil((3 + 9*len + 7) / 8) + trailer, rounded up to 16.  zlib: 2 + 4, raw: 0 + 0, gzip: 10 + 8
+    const uint64_t frame = container == HDLZ_CONTAINER_GZIP ? 18ull : container == HDLZ_CONTAINER_RAW ? 0ull : 6ull;
+    uint64_t b = frame + (3ull + 9ull * len + 7ull + 7ull) / 8ull;
     return (uint32_t)((b + 15ull) & ~15ull);
 }
 

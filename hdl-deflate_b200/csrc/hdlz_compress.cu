@@ -137,7 +137,7 @@ template <int kMaxMatch>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len,
            uint32_t uniform_len, uint8_t *__restrict__ out, uint64_t out_stride,
-           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue)
+           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue, uint32_t container)
 {
     extern __shared__ uint4 smem_raw[];
     uint32_t *LT = reinterpret_cast<uint32_t *>(smem_raw);
@@ -170,7 +170,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         const uint32_t L = in_len ? in_len[sid] : uniform_len;
         const uint8_t *src = in + sid * in_stride;
         uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + sid * out_stride);
-        if (L < HDLZ_MIN_INPUT || (uint64_t)compress_bound(L) > out_stride) {
+        if (L < HDLZ_MIN_INPUT || (uint64_t)compress_bound(L, container) > out_stride) {
             if (lane == 0) {
                 out_len[sid] = 0;
                 if (status) status[sid] = L < HDLZ_MIN_INPUT ? HDLZ_ST_SHORT_INPUT : HDLZ_ST_OUT_OVERFLOW;
@@ -181,9 +181,22 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 
         uint32_t carry = 0;              // positions of the next tile still covered by the last token
         uint32_t adler_a = 1, adler_b = 0;
-        uint32_t pw = 0x78u | (0x9Cu << 8) | (3u << 16);   // partial output word: header + BFINAL/BTYPE=01
+        // partial output word: container header + BFINAL/BTYPE=01 (zlib: 78 9C, deflate.py:753-761)
+        uint32_t pw = 0x78u | (0x9Cu << 8) | (3u << 16);
         uint32_t lbit = 19;              // valid bits in pw
         uint32_t wbase = 0;              // 32-bit words of the stream already written to HBM
+        if (container == HDLZ_CONTAINER_RAW) {
+            pw = 3u;
+            lbit = 3;
+        } else if (container == HDLZ_CONTAINER_GZIP) {
+            // 1F 8B 08 00 | MTIME 0 | XFL 0, OS FF (RFC 1952): eight bytes go out now, two ride in pw
+            if (lane == 0) {
+                dst32[0] = 0x00088B1Fu;
+                dst32[1] = 0u;
+            }
+            pw = (0xFFu << 8) | (3u << 16);
+            wbase = 2;
+        }
 
         for (uint32_t t0 = 0; t0 < L; t0 += kTile) {
             const bool last_tile = t0 + kTile >= L;
@@ -406,18 +419,29 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             } else {
                 total += 7;                                   // EOB: seven zero bits (deflate.py:772-779)
                 const uint32_t nbytes = (total + 7) >> 3;     // pad to a byte (deflate.py:784-787)
+                uint32_t trailer = 4;
                 if (lane == 0) {
                     uint8_t *ob = reinterpret_cast<uint8_t *>(outw);
-                    ob[nbytes + 0] = (uint8_t)(adler_b >> 8); // Adler-32 big-endian (deflate.py:788-814)
-                    ob[nbytes + 1] = (uint8_t)(adler_b & 255);
-                    ob[nbytes + 2] = (uint8_t)(adler_a >> 8);
-                    ob[nbytes + 3] = (uint8_t)(adler_a & 255);
+                    if (container == HDLZ_CONTAINER_ZLIB) {
+                        ob[nbytes + 0] = (uint8_t)(adler_b >> 8); // Adler-32 big-endian (deflate.py:788-814)
+                        ob[nbytes + 1] = (uint8_t)(adler_b & 255);
+                        ob[nbytes + 2] = (uint8_t)(adler_a >> 8);
+                        ob[nbytes + 3] = (uint8_t)(adler_a & 255);
+                    } else if (container == HDLZ_CONTAINER_GZIP) {
+                        // CRC-32 (filled in by k_gzip_crc, which reads the input once more) and ISIZE
+                        for (int b = 0; b < 4; ++b) {
+                            ob[nbytes + b] = 0;
+                            ob[nbytes + 4 + b] = (uint8_t)(L >> (8 * b));
+                        }
+                    }
                 }
+                if (container == HDLZ_CONTAINER_RAW) trailer = 0;
+                else if (container == HDLZ_CONTAINER_GZIP) trailer = 8;
                 __syncwarp();
-                const uint32_t nwords = (nbytes + 4 + 3) >> 2;
+                const uint32_t nwords = (nbytes + trailer + 3) >> 2;
                 for (uint32_t k = lane; k < nwords; k += 32) dst32[wbase + k] = outw[k];
                 if (lane == 0) {
-                    out_len[sid] = 4 * wbase + nbytes + 4;
+                    out_len[sid] = 4 * wbase + nbytes + trailer;
                     if (status) status[sid] = HDLZ_OK;
                 }
             }
@@ -453,12 +477,16 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     HDLZ_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
     if (ctx->max_match == 5)
         k_compress<5><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
-                                                                               d_out, out_stride, d_out_len, d_status, n, queue);
+                                                                               d_out, out_stride, d_out_len, d_status, n, queue,
+                                                                               ctx->container);
     else
         k_compress<10><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
-                                                                                d_out, out_stride, d_out_len, d_status, n, queue);
+                                                                                d_out, out_stride, d_out_len, d_status, n, queue,
+                                                                                ctx->container);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
+    if (ctx->container == HDLZ_CONTAINER_GZIP)
+        return launch_gzip_trailers(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, n, s);
     return HDLZ_SUCCESS;
 }
 

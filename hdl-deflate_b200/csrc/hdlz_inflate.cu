@@ -22,6 +22,7 @@
 // ordered by __syncwarp).  Algorithmic HBM traffic per stream: C bytes read + L bytes written.
 
 #include "hdlz_common.cuh"
+#include "hdlz_frame.cuh"
 
 namespace hdlz {
 namespace {
@@ -215,6 +216,8 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
     if (n_items == 0) return;
     __shared__ WarpSmem s_warp[kWarps];
     __shared__ FixedSmem s_fixed;
+    __shared__ uint32_t s_nib[16];        // CRC-32 nibble table (gzip trailer check)
+    if (threadIdx.x < 16) s_nib[threadIdx.x] = crc32_nibble_entry(threadIdx.x);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     WarpSmem &ws = s_warp[warp];
@@ -258,15 +261,12 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
     r.base = src - r.mis;
     r.end = r.mis + n_in;
 
-    if (n_in < 2) {
-        st = HDLZ_ST_TRUNCATED;
-    } else if (flags & HDLZ_F_VERIFY_HEADER) {
-        const uint32_t cmf = src[0], flg = src[1];
-        if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u || (flg & 0x20u)) st = HDLZ_ST_BAD_HEADER;
-    }
+    // container: zlib (the reference's, header skipped: di = 2, deflate.py:644), raw deflate or gzip
+    const Frame frame = parse_frame(src, n_in, flags);
+    st = frame.status;
 
     if (st == HDLZ_OK) {
-        r.seek(2);                                   // skip the zlib header: di = 2 (deflate.py:644)
+        r.seek(frame.body);
         const int64_t limit = 8 * (int64_t)n_in;
         const uint32_t wi_guard = (r.end + 8) / 4 + 2;   // words past the stream end: stop a runaway decode
         uint32_t final_blk = 0;
@@ -391,12 +391,19 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
 
         flush_literals();
         if (st == HDLZ_OK) {
-            // Adler-32 trailer: four bytes after the next byte boundary must exist ("NO EOF!", deflate.py:1535-1539)
+            // the trailer (zlib: Adler-32, four bytes) must exist after the next byte boundary ("NO EOF!",
+            // deflate.py:1535-1539)
             const int64_t bp = r.bitpos();
             const uint32_t tp = (uint32_t)((bp + 7) >> 3);
-            if (bp > limit || (uint64_t)tp + 4 > n_in) {
+            if (bp > limit || (uint64_t)tp + frame.trailer > n_in) {
                 st = HDLZ_ST_TRUNCATED;
-            } else if (flags & HDLZ_F_VERIFY_ADLER) {
+            } else if ((flags & HDLZ_F_VERIFY_ADLER) && (flags & HDLZ_F_GZIP)) {
+                // gzip: CRC-32 and ISIZE (RFC 1952); one lane walks the output
+                __syncwarp();
+                uint32_t bad = 0;
+                if (lane == 0) bad = crc32_bytes(dst, o, s_nib) != load_le32(src + tp) || o != load_le32(src + tp + 4);
+                if (__shfl_sync(HDLZ_FULL_MASK, bad, 0)) st = HDLZ_ST_BAD_CRC;
+            } else if ((flags & HDLZ_F_VERIFY_ADLER) && !(flags & HDLZ_F_RAW)) {
                 __syncwarp();
                 uint64_t s1 = 0, s2 = 0;
                 for (uint32_t i = lane; i < o; i += 32) {

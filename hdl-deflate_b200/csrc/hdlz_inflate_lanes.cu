@@ -28,6 +28,7 @@
 // Algorithmic HBM traffic per stream: C bytes read + L bytes written.
 
 #include "hdlz_common.cuh"
+#include "hdlz_frame.cuh"
 
 namespace hdlz {
 
@@ -180,6 +181,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     __shared__ uint32_t s_dist[32];       // fixed tree: 5 stream bits -> distance entry
     __shared__ uint32_t s_sym[288];       // literal/length symbol -> entry without code length
     __shared__ uint32_t s_dsym[32];       // distance symbol -> distance entry
+    __shared__ uint32_t s_nib[16];        // CRC-32 nibble table (gzip trailer check)
     __shared__ uint2 s_pat[8];            // min(distance, 4) -> {bytes of the source word to keep, replication factor}
     __shared__ unsigned long long s_mask8[9];   // n -> mask of the low n bytes
     __shared__ unsigned long long s_mult8[9];   // min(distance, 8) -> factor that repeats the low `distance` bytes over 8
@@ -191,6 +193,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         s_dist[threadIdx.x] = fixed_dist_entry(threadIdx.x);
         s_dsym[threadIdx.x] = fixed_dist_entry(__brev(threadIdx.x) >> 27);
     }
+    if (threadIdx.x < 16) s_nib[threadIdx.x] = crc32_nibble_entry(threadIdx.x);
     if (threadIdx.x < 9) {
         const uint32_t d = threadIdx.x;
         s_mask8[d] = d == 0 ? 0ull : d == 8 ? ~0ull : (1ull << (8 * d)) - 1ull;
@@ -218,7 +221,11 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     LaneScratch *my = (kDyn && scratch) ? scratch + gtid : nullptr;
     bool to_dyn = false;            // hand this stream to the dynamic-capable instantiation
 
-    const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) != 0;
+    // the container checksum, only on request: Adler-32 rides along with the appends, the CRC-32 of a gzip
+    // member is taken over the finished output
+    const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) && !(flags & (HDLZ_F_RAW | HDLZ_F_GZIP));
+    const bool want_crc = (flags & HDLZ_F_VERIFY_ADLER) && (flags & HDLZ_F_GZIP);
+    const uint32_t trailer_bytes = (flags & HDLZ_F_RAW) ? 0u : (flags & HDLZ_F_GZIP) ? 8u : 4u;
     uint32_t state = S_IDLE;
 
     // per-stream state
@@ -374,19 +381,23 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 if ((reinterpret_cast<uintptr_t>(src) & 3u) || (reinterpret_cast<uintptr_t>(dst) & 15u)) {
                     hand_over = true;                  // the warp-per-stream kernel takes any alignment
                     state = S_FINISH;
-                } else if (n_in < 2) {
-                    fail(HDLZ_ST_TRUNCATED);
-                } else if (flags & HDLZ_F_VERIFY_HEADER) {
-                    const uint32_t cmf = src[0], flg = src[1];
-                    if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u || (flg & 0x20u))
-                        fail(HDLZ_ST_BAD_HEADER);
-                }
-                if (state == S_HEADER) {
-                    tailw = 0;
-                    for (uint32_t b = 0; b < (n_in & 3u); ++b) tailw |= (uint32_t)src[4 * nfull + b] << (8 * b);
-                    acc = (uint64_t)(load_word(0) >> 16);      // skip the zlib header: di = 2 (deflate.py:644)
-                    nextw = load_word(1);
-                    ring[0] = 0;
+                } else {
+                    // container header: zlib (skipped like the reference does: di = 2, deflate.py:644),
+                    // none, or gzip
+                    const Frame frame = parse_frame(src, n_in, flags);
+                    if (frame.status != HDLZ_OK) {
+                        fail(frame.status);
+                    } else {
+                        tailw = 0;
+                        for (uint32_t b = 0; b < (n_in & 3u); ++b) tailw |= (uint32_t)src[4 * nfull + b] << (8 * b);
+                        const uint32_t skip = 8u * (frame.body & 3u);
+                        wi = frame.body >> 2;
+                        acc = (uint64_t)(load_word(wi) >> skip);
+                        fill = 32u - skip;
+                        ++wi;
+                        nextw = load_word(wi);
+                        ring[0] = 0;
+                    }
                 }
             }
             }
@@ -639,9 +650,12 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     for (uint32_t x = flushed; x < wo; ++x) dst32[x] = ring[(x & (kRing - 1)) * 32];
                     for (uint32_t k = 0; k < (o & 3u); ++k) dst[(o & ~3u) + k] = (uint8_t)(cw >> (8 * k));
                     const uint64_t bp = (uint64_t)wi * 32 - fill;
-                    const uint64_t tp = (bp + 7) >> 3;                       // Adler-32 trailer must be present
-                    if (bp > 8ull * n_in || tp + 4 > n_in) {
+                    const uint64_t tp = (bp + 7) >> 3;                       // the trailer (zlib: Adler-32) must be present
+                    if (bp > 8ull * n_in || tp + trailer_bytes > n_in) {
                         st = HDLZ_ST_TRUNCATED;                              // "NO EOF!" (deflate.py:1535-1539)
+                    } else if (want_crc) {
+                        if (crc32_bytes(dst, o, s_nib) != load_le32(src + tp) || o != load_le32(src + tp + 4))
+                            st = HDLZ_ST_BAD_CRC;
                     } else if (want_adler) {
                         ad_a %= 65521u; ad_b %= 65521u;
                         const uint32_t want = ((uint32_t)src[tp] << 24) | ((uint32_t)src[tp + 1] << 16) |

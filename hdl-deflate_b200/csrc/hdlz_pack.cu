@@ -4,6 +4,7 @@
 // (SURVEY.md 8(f) rank 2 "output compaction + block index").  Starts are 4-byte aligned.
 
 #include "hdlz_common.cuh"
+#include "hdlz_frame.cuh"
 
 namespace hdlz {
 namespace {
@@ -59,7 +60,39 @@ k_pack(const uint8_t *__restrict__ slots, uint64_t stride, const uint32_t *__res
     }
 }
 
+// gzip container: CRC-32 of every input stream into the trailer slot k_compress left (the eight
+// bytes before the end of the stream: CRC-32 | ISIZE).  One thread per stream; only runs when the
+// gzip container is selected.
+__global__ void __launch_bounds__(128)
+k_gzip_crc(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len, uint32_t uniform_len,
+           uint8_t *__restrict__ out, uint64_t out_stride, const uint32_t *__restrict__ out_len, uint64_t n)
+{
+    __shared__ uint32_t s_nib[16];
+    if (threadIdx.x < 16) s_nib[threadIdx.x] = crc32_nibble_entry(threadIdx.x);
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t olen = out_len[i];
+    if (olen < 18) return;                                   // the stream was not produced (status says why)
+    const uint32_t L = in_len ? in_len[i] : uniform_len;
+    const uint32_t crc = crc32_bytes(in + i * in_stride, L, s_nib);
+    uint8_t *t = out + i * out_stride + olen - 8;
+    for (int b = 0; b < 4; ++b) t[b] = (uint8_t)(crc >> (8 * b));
+}
+
 }  // namespace
+
+int launch_gzip_trailers(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                         uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, const uint32_t *d_out_len,
+                         uint64_t n, cudaStream_t s)
+{
+    if (n == 0) return HDLZ_SUCCESS;
+    k_gzip_crc<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, in_stride, d_in_len, uniform_len, d_out, out_stride,
+                                                           d_out_len, n);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
 
 int launch_pack(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
                 uint64_t *d_off, uint64_t *d_total, uint64_t n, cudaStream_t s)

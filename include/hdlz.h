@@ -65,12 +65,23 @@ typedef enum hdlz_status {
     HDLZ_ST_OUT_OVERFLOW = 6, /* output does not fit out_cap / out_stride (reference: ring back-pressure, deflate.py:1531,1597) */
     HDLZ_ST_BAD_STORED = 7,   /* stored block LEN != ~NLEN (reference does not check; zlib does)            */
     HDLZ_ST_BAD_HEADER = 8,   /* zlib CMF/FLG invalid — only with HDLZ_F_VERIFY_HEADER (reference skips it, deflate.py:644,665-676) */
-    HDLZ_ST_BAD_ADLER = 9     /* Adler-32 mismatch — only with HDLZ_F_VERIFY_ADLER (reference never checks, deflate.py:1535)       */
+    HDLZ_ST_BAD_ADLER = 9,    /* Adler-32 mismatch — only with HDLZ_F_VERIFY_ADLER (reference never checks, deflate.py:1535)       */
+    HDLZ_ST_BAD_CRC = 10      /* gzip CRC-32 / ISIZE mismatch — only with HDLZ_F_GZIP | HDLZ_F_VERIFY_ADLER                        */
 } hdlz_status;
 
 /* decompress flags */
-#define HDLZ_F_VERIFY_HEADER 1u
-#define HDLZ_F_VERIFY_ADLER 2u
+#define HDLZ_F_VERIFY_HEADER 1u /* zlib: check CMF/FLG (the reference skips the two bytes, deflate.py:644)           */
+#define HDLZ_F_VERIFY_ADLER 2u  /* check the container checksum: Adler-32 (zlib) or CRC-32 + ISIZE (gzip)             */
+#define HDLZ_F_RAW 4u           /* input is a bare RFC 1951 stream: no header, no trailer                              */
+#define HDLZ_F_GZIP 8u          /* input is one RFC 1952 (gzip) member; header always checked, optional fields skipped */
+
+/* Container written / read around the deflate body.  The reference knows zlib only (header bytes
+ * deflate.py:753-757, Adler-32 :788-814); raw and gzip wrap the SAME body (README.md:2 "(g)zip / zlib"). */
+typedef enum hdlz_container {
+    HDLZ_CONTAINER_ZLIB = 0,   /* 78 9C | body | Adler-32 (big-endian)                       — the default      */
+    HDLZ_CONTAINER_RAW = 1,    /* body only                                                                     */
+    HDLZ_CONTAINER_GZIP = 2    /* 1F 8B 08 00 00000000 00 FF | body | CRC-32 | ISIZE (little-endian)            */
+} hdlz_container;
 
 typedef struct hdlz_ctx hdlz_ctx;
 
@@ -96,6 +107,13 @@ uint32_t hdlz_compress_bound(uint32_t len);
  * with the same setting (FAST = True, CWINDOW = 32). */
 int hdlz_set_match10(hdlz_ctx *ctx, int match10);
 int hdlz_get_match10(hdlz_ctx *ctx);
+
+/* Container of every later compress call of the context (hdlz_container; default zlib, the
+ * reference's).  The deflate body is the same bits in all three.  hdlz_compress_bound_ex is the
+ * slot size a stream of `len` bytes needs in the given container (hdlz_compress_bound = zlib). */
+int hdlz_set_container(hdlz_ctx *ctx, int container);
+int hdlz_get_container(hdlz_ctx *ctx);
+uint32_t hdlz_compress_bound_ex(uint32_t len, int container);
 
 /* ---- compress: STARTC job (deflate.py:618-633; CSTATIC/SEARCH/SEARCHF/DISTANCE/CHECKSUM :734-1016) ----
  * Block i = d_in[i*in_stride .. +len_i), len_i = d_in_len ? d_in_len[i] : uniform_len
