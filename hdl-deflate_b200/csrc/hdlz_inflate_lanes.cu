@@ -267,8 +267,9 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     auto flush8 = [&]() {
         while ((o >> 2) - flushed >= 8u) {
             uint32_t q[8];
+            const uint32_t *g8 = ring + (flushed & (kRing - 1)) * 32;     // `flushed` is a multiple of 8: no wrap inside a group
 #pragma unroll
-            for (int k = 0; k < 8; ++k) q[k] = ring[((flushed + k) & (kRing - 1)) * 32];
+            for (int k = 0; k < 8; ++k) q[k] = g8[k * 32];
             uint4 *g = reinterpret_cast<uint4 *>(dst32 + flushed);
             g[0] = make_uint4(q[0], q[1], q[2], q[3]);
             g[1] = make_uint4(q[4], q[5], q[6], q[7]);
