@@ -256,6 +256,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
             }
             if (L - 2 < t0 + kTile + 32) {                   // R[q] = 0 for q >= L - 2
+                __syncwarp();                                // other lanes wrote these words in phase A
                 for (int i = (int)(L - 2 > t0 ? L - 2 - t0 : 0) + lane; i < kTile + 32; i += 32) Rw[i + (i >> 5)] = 0;
             }
             __syncwarp();
