@@ -545,8 +545,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 }
             }
             if (state == S_DYN && rem != 0) {
-                const uint32_t m = rem < 4u ? rem : 4u;
-                append(source(dist), m);
+                const uint32_t m = rem < 8u ? rem : 8u;                     // eight bytes per trip, as in fixed blocks
+                append8(source8(dist), m);
                 rem -= m;
             }
         } else if (state == S_HEADER) {
