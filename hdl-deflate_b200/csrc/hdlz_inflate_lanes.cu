@@ -18,9 +18,10 @@
 //     from global memory.
 //   - the dynamic-capable instantiation is persistent: when all lanes of a warp are between streams
 //     they take their next 32 streams together;
-//   - dynamic blocks: every resident thread owns a 2.5 KiB scratch in global memory (9-bit literal/
-//     length and 8-bit distance primary tables + canonical arrays for longer codes) that stays
-//     L2-resident; the lane parses the block header and builds its tables by itself (plain scalar
+//   - dynamic blocks: every resident thread owns a 1.8 KiB scratch in global memory (8-bit literal/
+//     length and 7-bit distance primary tables + canonical arrays for longer codes; smaller tables
+//     keep more of them in L2: 9 -> 8 bits took config 4 from 59 to 68 GB/s, 7 bits lose it to the slow
+//     path); the lane parses the block header and builds its tables by itself (plain scalar
 //     code, all lanes of a warp usually do it at the same time);
 //   - a stream the lanes cannot take (unaligned buffers, no scratch) is appended to a device work
 //     list that the warp-per-stream kernel (hdlz_inflate.cu) consumes.
@@ -41,10 +42,10 @@ namespace {
 
 constexpr int kLWarps = 4;
 constexpr int kLaneCtasPerSm = 10;     // fixed/stored instantiation (48 registers)
-constexpr int kDynCtasPerSm = 6;       // dynamic-capable instantiation (80 registers, 2.5 KiB of scratch per thread)
-constexpr int kRing = 32;   // words per lane (31 usable: the slot after the partial word is scratch)
-constexpr int kDynLitBits = 9;
-constexpr int kDynDistBits = 8;
+constexpr int kDynCtasPerSm = 6;       // dynamic-capable instantiation (80 registers, 1.8 KiB of scratch per thread)
+constexpr int kRing = 32;   // words per lane (30 usable: the two slots after the partial word are scratch)
+constexpr int kDynLitBits = 8;
+constexpr int kDynDistBits = 7;
 
 // per resident thread, global memory.  Table entry: (symbol << 4) | code length, 0 = longer code.
 struct LaneScratch {
@@ -54,6 +55,8 @@ struct LaneScratch {
     uint16_t sorted_d[32];
     uint16_t cnt_l[16];
     uint16_t cnt_d[16];
+    uint16_t resume_l[2];
+    uint16_t resume_d[2];
     uint8_t lens[320];
 };
 
@@ -109,7 +112,7 @@ __device__ uint32_t sym_entry(uint32_t sym)
 // thread in its scratch.  Returns 0, or 1 for an over-subscribed / illegally incomplete code
 // (zlib's inflate_table rules).
 __device__ __noinline__ int lane_build(const uint8_t *lens, int nsym, uint16_t *tbl, int tbits, uint16_t *cnt,
-                                       uint16_t *sorted, bool allow_incomplete)
+                                       uint16_t *sorted, uint16_t *resume, bool allow_incomplete)
 {
     uint16_t first[16], offs[16], run[16];
     for (int l = 0; l < 16; ++l) { cnt[l] = 0; run[l] = 0; }
@@ -132,6 +135,10 @@ __device__ __noinline__ int lane_build(const uint8_t *lens, int nsym, uint16_t *
         code = (code + cnt[l]) << 1;
         off += cnt[l];
     }
+    // where the bit-serial decode of a code longer than the table resumes: its `first` / `index` after
+    // the lengths 1 .. tbits have been ruled out
+    resume[0] = tbits < 15 ? first[tbits + 1] : 0;
+    resume[1] = tbits < 15 ? offs[tbits + 1] : 0;
     for (int s = 0; s < nsym; ++s) {
         const uint32_t l = lens[s];
         if (!l) continue;
@@ -146,11 +153,13 @@ __device__ __noinline__ int lane_build(const uint8_t *lens, int nsym, uint16_t *
     return 0;
 }
 
-// code longer than the primary table: canonical decode one bit at a time.  -> (sym << 4) | len, 0 = invalid
-__device__ __noinline__ uint32_t lane_slow_decode(uint32_t bits, const uint16_t *cnt, const uint16_t *sorted)
+// code longer than the primary table: canonical decode one bit at a time, starting after the `tbits`
+// bits the table has already ruled out.  -> (sym << 4) | len, 0 = invalid
+__device__ __noinline__ uint32_t lane_slow_decode(uint32_t bits, const uint16_t *cnt, const uint16_t *sorted, int tbits,
+                                                  const uint16_t *resume)
 {
-    int code = 0, first = 0, index = 0;
-    for (int l = 1; l <= 15; ++l) {
+    int code = (int)((__brev(bits) >> (32 - tbits)) << 1), first = resume[0], index = resume[1];
+    for (int l = tbits + 1; l <= 15; ++l) {
         code |= (int)((bits >> (l - 1)) & 1u);
         const int c = cnt[l];
         if (code - c < first) return ((uint32_t)sorted[index + (code - first)] << 4) | (uint32_t)l;
@@ -496,7 +505,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t x = (uint32_t)(acc >> used);
                         e = my->lit[x & ((1u << kDynLitBits) - 1u)];
-                        if ((e & 15u) == 0) e = lane_slow_decode(x, my->cnt_l, my->sorted_l);
+                        if ((e & 15u) == 0) e = lane_slow_decode(x, my->cnt_l, my->sorted_l, kDynLitBits, my->resume_l);
                         const uint32_t nb = e & 15u;
                         if (nb == 0 || (e >> 4) >= 256u || used + nb > 32u || nlit >= room) break;
                         lits |= (e >> 4) << (8 * k);
@@ -528,7 +537,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                             if (fill < 32) refill();
                             const uint32_t y = (uint32_t)acc;
                             uint32_t d = my->dist[y & ((1u << kDynDistBits) - 1u)];
-                            if ((d & 15u) == 0) d = lane_slow_decode(y, my->cnt_d, my->sorted_d);
+                            if ((d & 15u) == 0) d = lane_slow_decode(y, my->cnt_d, my->sorted_d, kDynDistBits, my->resume_d);
                             const uint32_t dnb = d & 15u;
                             const uint32_t de = s_dsym[(d >> 4) & 31u];
                             const uint32_t deb = de & 15u;
@@ -593,8 +602,9 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 uint8_t *lens = my->lens;
                 for (int i = 0; i < 19; ++i) lens[i] = 0;
                 for (uint32_t i = 0; i < ncode; ++i) lens[c_clorder[i]] = (uint8_t)get(3);
-                // code-length code: 7-bit table in the (not yet built) distance table area
-                if (!bad) bad = lane_build(lens, 19, my->dist, 7, my->cnt_d, my->sorted_d, false);
+                // code-length code: 7-bit table in the (not yet used) sorted-symbols area of the literal code
+                uint16_t *cl_tbl = my->sorted_l;
+                if (!bad) bad = lane_build(lens, 19, cl_tbl, 7, my->cnt_d, my->sorted_d, my->resume_d, false);
                 if (!bad) {
                     uint32_t any = 0;
                     for (int l = 1; l <= 7; ++l) any |= my->cnt_d[l];
@@ -609,7 +619,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         if (wi > nfull + 2) { bad = 2; break; }
                         refill();
                     }
-                    const uint32_t e = my->dist[(uint32_t)acc & 127u];
+                    const uint32_t e = cl_tbl[(uint32_t)acc & 127u];
                     const uint32_t nb = e & 15u, sym = e >> 4;
                     if (nb == 0) { bad = 1; break; }
                     acc >>= nb; fill -= nb;
@@ -625,8 +635,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     idx += rep;
                 }
                 if (!bad && ll[256] == 0) bad = 1;                           // no end-of-block code
-                if (!bad) bad = lane_build(ll + nlen, (int)ndist, my->dist, kDynDistBits, my->cnt_d, my->sorted_d, true);
-                if (!bad) bad = lane_build(ll, (int)nlen, my->lit, kDynLitBits, my->cnt_l, my->sorted_l, true);
+                if (!bad) bad = lane_build(ll + nlen, (int)ndist, my->dist, kDynDistBits, my->cnt_d, my->sorted_d, my->resume_d, true);
+                if (!bad) bad = lane_build(ll, (int)nlen, my->lit, kDynLitBits, my->cnt_l, my->sorted_l, my->resume_l, true);
                 if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
                 else state = S_DYN;
             }
