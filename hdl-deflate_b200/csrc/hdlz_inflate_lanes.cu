@@ -48,9 +48,14 @@ constexpr int kDynLitBits = 8;
 constexpr int kDynDistBits = 7;
 
 // per resident thread, global memory.  Table entry: (symbol << 4) | code length, 0 = longer code.
-struct LaneScratch {
+// The primary tables every symbol goes through live in their own array (one LaneHot per resident
+// thread) so that the launch can ask the L2 to keep exactly that range (access-policy window).
+struct LaneHot {
     uint16_t lit[1 << kDynLitBits];
     uint16_t dist[1 << kDynDistBits];
+};
+
+struct LaneScratch {
     uint16_t sorted_l[288];
     uint16_t sorted_d[32];
     uint16_t cnt_l[16];
@@ -182,7 +187,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, uint32_t flags,
                 uint32_t *__restrict__ work_list, uint32_t *__restrict__ work_count,
                 uint32_t *__restrict__ dyn_list, uint32_t *__restrict__ dyn_count,
-                const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, LaneScratch *scratch)
+                const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, LaneScratch *scratch,
+                LaneHot *hot_base)
 {
     const uint64_t n_items = items ? (uint64_t)*item_count : n_streams;
     if (n_items == 0) return;
@@ -228,6 +234,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     uint64_t sid = 0;
     uint32_t *ring = &s_ring[threadIdx.x >> 5][0][threadIdx.x & 31];     // word k at ring[k * 32]
     LaneScratch *my = (kDyn && scratch) ? scratch + gtid : nullptr;
+    LaneHot *hot = (kDyn && scratch) ? hot_base + gtid : nullptr;
     bool to_dyn = false;            // hand this stream to the dynamic-capable instantiation
 
     // the container checksum, only on request: Adler-32 rides along with the appends, the CRC-32 of a gzip
@@ -504,7 +511,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     // up to four literals (or stop at the first other symbol)
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t x = (uint32_t)(acc >> used);
-                        e = my->lit[x & ((1u << kDynLitBits) - 1u)];
+                        e = hot->lit[x & ((1u << kDynLitBits) - 1u)];
                         if ((e & 15u) == 0) e = lane_slow_decode(x, my->cnt_l, my->sorted_l, kDynLitBits, my->resume_l);
                         const uint32_t nb = e & 15u;
                         if (nb == 0 || (e >> 4) >= 256u || used + nb > 32u || nlit >= room) break;
@@ -536,7 +543,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                             acc >>= nb + eb; fill -= nb + eb;
                             if (fill < 32) refill();
                             const uint32_t y = (uint32_t)acc;
-                            uint32_t d = my->dist[y & ((1u << kDynDistBits) - 1u)];
+                            uint32_t d = hot->dist[y & ((1u << kDynDistBits) - 1u)];
                             if ((d & 15u) == 0) d = lane_slow_decode(y, my->cnt_d, my->sorted_d, kDynDistBits, my->resume_d);
                             const uint32_t dnb = d & 15u;
                             const uint32_t de = s_dsym[(d >> 4) & 31u];
@@ -635,8 +642,8 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     idx += rep;
                 }
                 if (!bad && ll[256] == 0) bad = 1;                           // no end-of-block code
-                if (!bad) bad = lane_build(ll + nlen, (int)ndist, my->dist, kDynDistBits, my->cnt_d, my->sorted_d, my->resume_d, true);
-                if (!bad) bad = lane_build(ll, (int)nlen, my->lit, kDynLitBits, my->cnt_l, my->sorted_l, my->resume_l, true);
+                if (!bad) bad = lane_build(ll + nlen, (int)ndist, hot->dist, kDynDistBits, my->cnt_d, my->sorted_d, my->resume_d, true);
+                if (!bad) bad = lane_build(ll, (int)nlen, hot->lit, kDynLitBits, my->cnt_l, my->sorted_l, my->resume_l, true);
                 if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
                 else state = S_DYN;
             }
@@ -714,7 +721,9 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
     // scratch for dynamic blocks: one slot per concurrent launch (the *_host pipelines run three)
     const int slot = lane_slot % 3;
     const uint64_t dyn_blocks = (uint64_t)ctx->sm_count * kDynCtasPerSm;
-    const size_t need = (size_t)dyn_blocks * (kLWarps * 32) * sizeof(LaneScratch);
+    const size_t dyn_threads = (size_t)dyn_blocks * (kLWarps * 32);
+    const size_t hot_bytes = dyn_threads * sizeof(LaneHot);
+    const size_t need = hot_bytes + dyn_threads * sizeof(LaneScratch);
     if (!(flags & HDLZ_F_NO_LANE_SCRATCH) && ctx->d_lane_cap[slot] < need) {
         if (ctx->d_lane[slot]) HDLZ_CUDA(cudaFree(ctx->d_lane[slot]));
         ctx->d_lane[slot] = nullptr;
@@ -722,18 +731,55 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
         if (cudaMalloc(&ctx->d_lane[slot], need) == cudaSuccess) ctx->d_lane_cap[slot] = need;
         else (void)cudaGetLastError();           // no scratch: dynamic streams go to the warp-per-stream kernel
     }
-    LaneScratch *scratch = (flags & HDLZ_F_NO_LANE_SCRATCH) ? nullptr : reinterpret_cast<LaneScratch *>(ctx->d_lane[slot]);
+    const bool have = !(flags & HDLZ_F_NO_LANE_SCRATCH) && ctx->d_lane[slot];
+    LaneHot *hot = have ? reinterpret_cast<LaneHot *>(ctx->d_lane[slot]) : nullptr;
+    LaneScratch *scratch = have ? reinterpret_cast<LaneScratch *>(static_cast<uint8_t *>(ctx->d_lane[slot]) + hot_bytes) : nullptr;
     k_inflate_lanes<false><<<(unsigned)blocks, kLWarps * 32, 0, s>>>(
         d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n, flags, list, count,
-        scratch ? dyn_list : nullptr, dyn_count, nullptr, nullptr, nullptr);
+        scratch ? dyn_list : nullptr, dyn_count, nullptr, nullptr, nullptr, nullptr);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     if (scratch) {
-        k_inflate_lanes<true><<<(unsigned)dyn_blocks, kLWarps * 32, 0, s>>>(
-            d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n, flags, list, count,
-            nullptr, nullptr, dyn_list, dyn_count, scratch);
+        // the primary tables are re-read for every symbol while inputs and outputs stream through the L2
+        // once: ask the L2 to keep the table range (as much of it as the device lets a window persist)
+        static int l2_persist[64] = {0}, l2_window[64] = {0};
+        const int dv = ctx->device & 63;
+        if (!l2_window[dv]) {
+            int v = 0;
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            l2_persist[dv] = v;
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+            l2_window[dv] = v > 0 ? v : -1;
+            if (l2_persist[dv] > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_persist[dv]);
+            (void)cudaGetLastError();
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)dyn_blocks);
+        cfg.blockDim = dim3(kLWarps * 32);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        unsigned nattr = 0;
+        if (l2_persist[dv] > 0 && l2_window[dv] > 0) {
+            const size_t win = hot_bytes < (size_t)l2_window[dv] ? hot_bytes : (size_t)l2_window[dv];
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = hot;
+            attr[0].val.accessPolicyWindow.num_bytes = win;
+            attr[0].val.accessPolicyWindow.hitRatio = win <= (size_t)l2_persist[dv] ? 1.0f : (float)l2_persist[dv] / (float)win;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            nattr = 1;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = nattr;
+        const uint32_t *no_list = nullptr;
+        uint32_t *no_out = nullptr;
+        HDLZ_CUDA(cudaLaunchKernelEx(&cfg, k_inflate_lanes<true>, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride,
+                                     out_cap, d_out_len, d_status, n, flags, list, count, no_out, no_out,
+                                     (const uint32_t *)dyn_list, (const uint32_t *)dyn_count, scratch, hot));
         ctx->launches++;
         HDLZ_CUDA(cudaGetLastError());
+        (void)no_list;
     }
     return launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
                                   d_status, n, flags, list, count, s);
