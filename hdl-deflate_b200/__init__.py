@@ -29,6 +29,7 @@ F_VERIFY_HEADER = 1
 F_VERIFY_ADLER = 2     # the container checksum: Adler-32 (zlib) or CRC-32 + ISIZE (gzip)
 F_RAW = 4              # decompress: bare RFC 1951 stream
 F_GZIP = 8             # decompress: one RFC 1952 member
+F_PERSIST_TABLES = 16  # decompress: keep the dynamic-block decode tables in the L2 (persisting carve-out)
 CONTAINER_ZLIB, CONTAINER_RAW, CONTAINER_GZIP = 0, 1, 2
 
 STATUS_NAMES = ("OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR", "TRUNCATED",

@@ -741,8 +741,11 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
     HDLZ_CUDA(cudaGetLastError());
     if (scratch) {
         // the primary tables are re-read for every symbol while inputs and outputs stream through the L2
-        // once: ask the L2 to keep the table range (as much of it as the device lets a window persist)
-        static int l2_persist[64] = {0}, l2_window[64] = {0};
+        // once.  With HDLZ_F_PERSIST_TABLES the launch asks the L2 to keep the table range (as much of it
+        // as the device lets a window persist).  The carve-out is a device-wide limit and costs the
+        // other kernels L2 capacity (the fixed-block kernel lost 10 % with 79 MB set aside), hence
+        // opt-in, and given back by the next call without the flag.
+        static int l2_persist[64] = {0}, l2_window[64] = {0}, l2_carved[64] = {0};
         const int dv = ctx->device & 63;
         if (!l2_window[dv]) {
             int v = 0;
@@ -750,8 +753,13 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
             l2_persist[dv] = v;
             cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
             l2_window[dv] = v > 0 ? v : -1;
-            if (l2_persist[dv] > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_persist[dv]);
             (void)cudaGetLastError();
+        }
+        const bool persist = (flags & HDLZ_F_PERSIST_TABLES) && l2_persist[dv] > 0 && l2_window[dv] > 0;
+        if (persist != (l2_carved[dv] != 0)) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist ? (size_t)l2_persist[dv] : 0);
+            (void)cudaGetLastError();
+            l2_carved[dv] = persist ? 1 : 0;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)dyn_blocks);
@@ -760,7 +768,7 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         unsigned nattr = 0;
-        if (l2_persist[dv] > 0 && l2_window[dv] > 0) {
+        if (persist) {
             const size_t win = hot_bytes < (size_t)l2_window[dv] ? hot_bytes : (size_t)l2_window[dv];
             attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
             attr[0].val.accessPolicyWindow.base_ptr = hot;

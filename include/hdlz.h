@@ -74,6 +74,8 @@ typedef enum hdlz_status {
 #define HDLZ_F_VERIFY_ADLER 2u  /* check the container checksum: Adler-32 (zlib) or CRC-32 + ISIZE (gzip)             */
 #define HDLZ_F_RAW 4u           /* input is a bare RFC 1951 stream: no header, no trailer                              */
 #define HDLZ_F_GZIP 8u          /* input is one RFC 1952 (gzip) member; header always checked, optional fields skipped */
+#define HDLZ_F_PERSIST_TABLES 16u /* batches of dynamic-Huffman streams: keep the per-stream decode tables in the L2
+                                  * (sets the device's persisting-L2 carve-out until the next call without the flag) */
 
 /* Container written / read around the deflate body.  The reference knows zlib only (header bytes
  * deflate.py:753-757, Adler-32 :788-814); raw and gzip wrap the SAME body (README.md:2 "(g)zip / zlib"). */

@@ -144,7 +144,7 @@ def test_routes_agree_on_mixed_and_corrupt_streams(engine, route):
             assert want is None or len(want) > 6000, (i, status[i])
 
 
-@pytest.mark.parametrize("route,n", [(0, 64), (FORCE_LANES, 64), (0, 1500)])
+@pytest.mark.parametrize("route,n", [(0, 64), (FORCE_LANES, 64), (0, 1500), (hz.F_PERSIST_TABLES, 1500)])
 def test_config4_dynamic_32k(engine, route, n):
     """BASELINE config 4 shape: 32 KiB plain, zlib level 6 dynamic trees, OBSIZE = 32768; through the
     warp-per-stream kernel (few streams) and the lane-per-stream kernel with per-lane tables (many)."""

@@ -130,7 +130,7 @@ def config4(eng, args):
     d_st = torch.zeros(n, dtype=torch.int32, device=dev)
 
     def run():
-        eng.decompress_batch(d_in, None, stride, d_len, d_out, L, L, d_olen, d_st, n, flags=0, stream=s)
+        eng.decompress_batch(d_in, None, stride, d_len, d_out, L, L, d_olen, d_st, n, flags=hz.F_PERSIST_TABLES, stream=s)
     ms, best = timed(run, args.steps)
     assert int(d_st.abs().sum()) == 0 and bool((d_olen == L).all())
     assert torch.equal(d_out.view(n, L), d_plain[sel]), "config4: output differs from the original"
