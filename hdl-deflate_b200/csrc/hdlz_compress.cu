@@ -4,24 +4,27 @@
 //
 //   persistent warps, one WARP per stream at a time, tiles of 1024 input positions;
 //   everything between the HBM read of the input and the HBM write of the stream lives
-//   in shared memory and registers.
+//   in shared memory and registers.  Streams are handed out through a device-wide queue
+//   head (one atomic per stream), not a static stride.
 //
 //   load     HBM -> shared with 128-bit cp.async (LDGSTS), 32 bytes of history and 32 bytes
 //            of look-ahead around the tile.
 //   phase A  lane <-> position (32 positions per step)
 //            R[p] = 32-bit mask, bit (32-d) <=> x[p-d] == x[p], d = 1..32.
-//            Inside a 32-chunk the equalities come from ONE match.any; against the
-//            previous chunk from a 256-entry per-warp table T[value] = lane mask of
-//            that value in the previous chunk; one funnel shift joins both halves.
+//            A 256-entry per-warp table T[value] = lane mask of that value: the lanes read
+//            the previous chunk's entry, clear the previous chunk's entries, OR their own bit
+//            in with a shared-memory atomic and read the entry back; one funnel shift joins
+//            both halves.  (Not MATCH.ANY: it costs 2 cycles of the SM-wide ADU pipe per
+//            distinct lane value and bound the whole kernel, profiles/r01_ubench_match.txt.)
 //            This replaces the 32 `matcher3` comparators + cwindow shift register
 //            (deflate.py:407-421, 442-453).  R[q] = 0 for q >= L-2 encodes all the
 //            `di < isize - k` guards of SEARCH/SEARCHF (deflate.py:913-952, 975-977).
 //            Adler-32 partial sums ride along (CSTATIC/CHECKSUM, :826-831, :884-897).
 //   phase B  lane <-> segment of 32 consecutive positions, walked from the back
 //            M3 = R[p] & R[p+1] & R[p+2]  -> 3-byte match at every distance at once;
-//            nearest distance = clz (lowest `si` first, deflate.py:982-988);
+//            nearest distance = highest set bit (lowest `si` first, deflate.py:982-988);
 //            length = 3 + leading run of that bit through R[p+3..p+9] (SEARCHF), counted
-//            by summing the surviving bit in a 64-bit accumulator (mad.wide on the FMA pipe);
+//            by summing the surviving bit in a 64-bit accumulator;
 //            token bits from two small LUTs (fixed Huffman, DISTANCE :836-882).
 //            The same backward walk runs the parse DP: h[j] = skip count left for
 //            the next segment if a token starts at j (10-nibble shift register).
