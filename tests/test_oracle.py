@@ -80,6 +80,24 @@ def test_restatement_matches_live_reference_fuzz():
         assert st == 0 and out == ref, (t, n, kind)
 
 
+@pytest.mark.skipif(not ref_sim.available(), reason="reference sources not present (GPU box)")
+def test_restatement_matches_live_reference_fuzz_match5():
+    """The same against the reference built with MATCH10 = False (deflate.py:34-35, 913-924)."""
+    rnd = random.Random(7)
+    for t in range(12):
+        n = rnd.choice([5, 8, 21, 64, 130, 400])
+        kind = t % 3
+        if kind == 0:
+            data = bytes(rnd.choice(b"ab") for _ in range(n))
+        elif kind == 1:
+            data = bytes(rnd.choice(b"abcdefgh") for _ in range(n))
+        else:
+            data = (bytes(rnd.randrange(256) for _ in range(5)) * (n // 5 + 1))[:n]
+        ref, _ = ref_sim.ref_compress(data, match10=False)
+        st, out = hdlz_oracle.compress(data, maxlen=5)
+        assert st == 0 and out == ref, (t, n, kind)
+
+
 def test_inflate_restatement_matches_zlib():
     rnd = random.Random(5)
     text = " ".join("   Hello World! %d     " % i for i in range(300)).encode()
