@@ -63,3 +63,28 @@ def test_product_never_imports_oracle():
                 checked += 1
                 assert not pat.search(open(os.path.join(dp, f)).read()), (dp, f)
     assert checked >= 8
+
+
+def test_c_client_builds_and_runs(tmp_path):
+    """include/hdlz.h is plain C: a C program compiles against it, links libhdlz.so and runs.  Without a
+    GPU the library answers the device-independent calls and refuses to create a context."""
+    import shutil
+    import subprocess
+    import torch
+    _built()
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from hdl_deflate_b200 import _native
+    libdir = os.path.dirname(_native.LIB_PATH)
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_example.c"), "-o", exe, "-L", libdir, "-lhdlz",
+                           "-Wl,-rpath," + libdir])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    out = p.stdout
+    assert p.returncode == 0, out + p.stderr
+    assert "version 000100" in out and "bound2048 2320 2320 2336" in out and "status4 DIST_TOO_FAR" in out
+    if torch.cuda.is_available():
+        assert "compress 0 status 0" in out and "head 789c" in out and "same 1" in out
+    else:
+        assert "devices 0" in out and "create -" in out

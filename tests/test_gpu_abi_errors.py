@@ -53,3 +53,22 @@ def test_options_round_trip(engine):
     engine.container = hz.CONTAINER_ZLIB
     assert hz.compress_bound(2048) == 2320 and hz.compress_bound(2048, hz.CONTAINER_RAW) == 2320 - 0
     assert hz.compress_bound(2048, hz.CONTAINER_GZIP) == 2336
+
+
+def test_c_client_runs_a_job(tmp_path):
+    """tests/c/abi_example.c (plain C against include/hdlz.h) compresses and inflates one stream."""
+    import os
+    import shutil
+    import subprocess
+    from hdl_deflate_b200 import _native
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_native.LIB_PATH)
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c", "abi_example.c"), "-o", exe, "-L", libdir, "-lhdlz",
+                           "-Wl,-rpath," + libdir])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "compress 0 status 0" in p.stdout and "head 789c" in p.stdout and "same 1" in p.stdout
