@@ -107,31 +107,48 @@ def ncu_traffic(kernel, n_blocks):
 # ----------------------------------------------------------------------------------------------
 # CPU arms: the oracle port (C restatement of deflate.py's compress + inflate) and host zlib
 # ----------------------------------------------------------------------------------------------
+def compress_bound_py(n):
+    """hdlz_compress_bound restated (2 + ceil((3 + 9n + 7) / 8) + 4, rounded up to 16): the CPU arms must not
+    load the product library."""
+    return ((6 + (3 + 9 * n + 7 + 7) // 8) + 15) & ~15
+
+
 def cpu_roundtrip(sample, nthreads, repeat=1):
-    """Time the port on `sample` (uint8 [n, 2048]) with `nthreads` threads.
-    -> (roundtrip GB/s as defined for `value`, compress GB/s, decompress GB/s, seconds)."""
+    """Time the CPU arm on `sample` (uint8 [n, 2048]) with `nthreads` threads: compress = the tuned port
+    of deflate.py's compressor (oracle/hdlz_oracle.c hdlz_oracle_compress_fast: SSE2 compares, 64-bit bit
+    buffer, zlib's adler32; same bytes as the plain restatement), decompress = the faster of the port's
+    inflate and host zlib's inflate.
+    -> dict(value, compress_gbps, decompress_gbps, seconds, inflate = which inflater won, ...)."""
     import numpy as np
     from oracle import hdlz_oracle as O
-    from hdl_deflate_b200 import compress_bound
     n = sample.shape[0]
-    ostride = compress_bound(BLOCK)
-    comp = np.empty((n, ostride), dtype=np.uint8)
-    back = np.empty((n, BLOCK), dtype=np.uint8)
+    ostride = compress_bound_py(BLOCK)
+    comp = np.zeros((n, ostride), dtype=np.uint8)
+    back = np.zeros((n, BLOCK), dtype=np.uint8)
     ioff = np.arange(n, dtype=np.uint64) * BLOCK
     ooff = np.arange(n, dtype=np.uint64) * ostride
     lens = np.full(n, BLOCK, dtype=np.uint32)
-    tc = td = 0.0
+    tc = tp = tz = 0.0
     for _ in range(repeat):
         t0 = time.perf_counter()
-        clen, st = O.batch(O.KIND_PORT_COMPRESS, sample, ioff, lens, comp, ooff, ostride, nthreads)
+        clen, st = O.batch(O.KIND_FAST_COMPRESS, sample, ioff, lens, comp, ooff, ostride, nthreads)
         t1 = time.perf_counter()
         blen, st2 = O.batch(O.KIND_PORT_INFLATE, comp, ooff, clen, back, ioff, BLOCK, nthreads)
         t2 = time.perf_counter()
+        assert not st.any() and not st2.any() and np.array_equal(back, sample)
+        t3 = time.perf_counter()
+        blen, st3 = O.batch(O.KIND_ZLIB_INFLATE, comp, ooff, clen, back, ioff, BLOCK, nthreads)
+        t4 = time.perf_counter()
+        assert not st3.any() and np.array_equal(back, sample)
         tc += t1 - t0
-        td += t2 - t1
-    assert not st.any() and not st2.any() and np.array_equal(back, sample)
+        tp += t2 - t1
+        tz += t4 - t3
+    td = min(tp, tz)
     byt = n * BLOCK * repeat
-    return 2 * byt / (tc + td) / 1e9, byt / tc / 1e9, byt / td / 1e9, tc + td
+    return {"value": 2 * byt / (tc + td) / 1e9, "compress_gbps": byt / tc / 1e9, "decompress_gbps": byt / td / 1e9,
+            "seconds": tc + tp + tz, "inflate": "zlib" if tz <= tp else "port",
+            "port_inflate_gbps": byt / tp / 1e9, "zlib_inflate_gbps": byt / tz / 1e9,
+            "kind": "port+zlib" if tz <= tp else "port"}
 
 
 def cpu_zlib(sample, nthreads):
@@ -171,8 +188,12 @@ def reference_sim_rate():
 
 
 def host_sample(n):
+    import importlib.util
     import numpy as np
-    from hdl_deflate_b200 import workload
+    # the pure-Python workload definition, loaded by path: importing the package would pull in the ctypes binding
+    spec = importlib.util.spec_from_file_location("hdlz_workload", os.path.join(ROOT, "hdl-deflate_b200", "workload.py"))
+    workload = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(workload)
     return np.frombuffer(b"".join(workload.blocks(0, n, BLOCK)), dtype=np.uint8).reshape(n, BLOCK)
 
 
@@ -182,8 +203,7 @@ def run_reference(args, rank, world):
     (oracle/hdlz_oracle.c, checked byte-for-byte against the executing reference) on all host threads."""
     if rank != 0:
         return
-    import __graft_entry__
-    __graft_entry__.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])     # the CPU arm only: no libhdlz.so here
     cores = os.cpu_count() or 1
     n = args.ref_blocks
     sample = host_sample(min(n, 4096))
@@ -194,25 +214,174 @@ def run_reference(args, rank, world):
         cpu_roundtrip(sample, cores)
     t0 = time.perf_counter()
     tot_c = tot_d = 0.0
+    r = None
     for _ in range(args.steps):
-        v, c, d, secs = cpu_roundtrip(sample, cores)
-        tot_c += n * BLOCK / c / 1e9
-        tot_d += n * BLOCK / d / 1e9
+        r = cpu_roundtrip(sample, cores)
+        tot_c += n * BLOCK / r["compress_gbps"] / 1e9
+        tot_d += n * BLOCK / r["decompress_gbps"] / 1e9
     t = time.perf_counter() - t0
     byt = n * BLOCK * args.steps
     value = 2 * byt / (tot_c + tot_d) / 1e9
-    sample_desc = "%d of the config's 2 KiB blocks per step (bounded sample), %d steps" % (n, args.steps)
+    sample_desc = "%d of the config's 2 KiB blocks per step (4096 distinct, tiled; bounded sample), %d steps" % (n, args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tot_c + tot_d) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args.blocks), "sample": sample_desc},
         "compress_gbps": byt / tot_c / 1e9, "decompress_gbps": byt / tot_d / 1e9,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample_desc,
+                         "what": "compress: tuned C port of deflate.py's FAST+MATCH10 compressor (bit-identical "
+                                 "output); decompress: the faster of the port's inflate and host zlib inflate (%s won: "
+                                 "port %.2f, zlib %.2f GB/s)" % (r["inflate"], r["port_inflate_gbps"], r["zlib_inflate_gbps"])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs[2] and [3] at full size (decompress-only), folded into the same JSON line.
+# Host zlib (Python's, on a thread pool) is only the fixture generator; the timed region is
+# hdlz_decompress_batch on resident device buffers (CUDA events, 3 warm-ups).
+# ----------------------------------------------------------------------------------------------
+def _zlib_many(rows, level, strategy, threads):
+    """Host-zlib streams of the rows of a uint8 [n, L] array, on all cores through tools/zfixture.c (built on
+    demand; plumbing, neither product nor oracle) -> (packed uint8 with 4-byte aligned starts, off i64, len u32)."""
+    import ctypes
+    import numpy as np
+    so = os.path.join(ROOT, "tools", "libzfixture.so")
+    src = os.path.join(ROOT, "tools", "zfixture.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src, "-lz", "-lpthread"])
+    lib = ctypes.CDLL(so)
+    lib.zfix_deflate_packed.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.POINTER(ctypes.c_uint64)]
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    n, L = rows.shape
+    cap = n * (L + L // 8 + 64) + 16
+    out = np.empty(cap, dtype=np.uint8)
+    off = np.zeros(n, dtype=np.uint64)
+    lens = np.zeros(n, dtype=np.uint32)
+    total = ctypes.c_uint64(0)
+    rc = lib.zfix_deflate_packed(rows.ctypes.data, n, L, level, strategy, threads, out.ctypes.data, cap, off.ctypes.data,
+                                 lens.ctypes.data, ctypes.byref(total))
+    assert rc == 0, "zfixture failed (%d)" % rc
+    return out[:total.value + 16], off.astype(np.int64), lens
+
+
+def _time_launches(fn, steps, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for k in range(steps):
+        fn()
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+    return sum(ts) / steps, min(ts)
+
+
+def run_config3(eng, hz, d_plain, n, dev, stream, steps, threads, peak):
+    """configs[2]: n x 2 KiB blocks as host-zlib Z_FIXED streams (level 6), packed with a 4-byte aligned
+    offset array, decompress-only; byte-exact against the blocks before anything is timed."""
+    import zlib
+    import torch
+    t0 = time.time()
+    plain = d_plain.view(n, BLOCK).cpu().numpy()
+    packed, off, lens = _zlib_many(plain, 6, zlib.Z_FIXED, threads)
+    t_fix = time.time() - t0
+    d_in = torch.from_numpy(packed).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_len = torch.from_numpy(lens.astype("int32")).to(dev)
+    d_out = torch.empty(n * BLOCK, dtype=torch.uint8, device=dev)
+    d_olen = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def run(flags=0):
+        eng.decompress_batch(d_in, d_off, 0, d_len, d_out, BLOCK, BLOCK, d_olen, d_st, n, flags=flags, stream=stream)
+    run(hz.F_VERIFY_ADLER)
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum()) == 0 and bool((d_olen == BLOCK).all()), "config3: status / length"
+    assert torch.equal(d_out, d_plain), "config3: output differs from the original blocks"
+    d_out.zero_()
+    ms, best = _time_launches(run, steps)
+    assert torch.equal(d_out, d_plain)
+    ms_v, _ = _time_launches(lambda: run(hz.F_VERIFY_ADLER), steps)
+    cbytes = int(lens.sum())
+    alg = cbytes + n * BLOCK
+    return {"workload": "BASELINE configs[2]: %d x 2 KiB host-zlib Z_FIXED streams (level 6, wbits 15), packed, 4-byte "
+                        "aligned offsets, decompress-only" % n,
+            "decompress_gbps": n * BLOCK / (ms * 1e-3) / 1e9, "decompress_gbps_verified": n * BLOCK / (ms_v * 1e-3) / 1e9,
+            "ms": ms, "ms_best": best, "compressed_ratio": cbytes / (n * BLOCK), "byte_exact_vs_original": True,
+            "roofline": {"bound": "hbm", "kernel": "k_inflate_lanes<0>", "achieved": alg / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": alg, "traffic": ncu_traffic("config3", n)},
+            "fixture_seconds": t_fix}
+
+
+def config4_plain(nd, L=32768, seed=4):
+    """Plain side of configs[3]: Zipf-like bytes over 64 symbols with repeats at distances up to 32 KiB
+    (SURVEY 8(d)); compressible enough that zlib level 6 emits dynamic blocks."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, 65) ** 1.1
+    p /= p.sum()
+    plain = rng.choice(64, size=(nd, L), p=p).astype(np.uint8) + 32
+    for _ in range(6):
+        src = rng.integers(0, L - 4096, nd)
+        dst = rng.integers(0, L - 4096, nd)
+        ln = rng.integers(64, 4096, nd)
+        for i in range(nd):
+            plain[i, dst[i]:dst[i] + ln[i]] = plain[i, src[i]:src[i] + ln[i]].copy()
+    return plain
+
+
+def run_config4(eng, hz, n, nd, dev, stream, steps, threads, peak):
+    """configs[3]: n x 32 KiB host-zlib level-6 (dynamic-tree) streams, drawn cyclically from nd distinct
+    ones (~200 MB compressed, beyond the L2), fixed-stride slots, OBSIZE = 32768, decompress-only."""
+    import numpy as np
+    import torch
+    L = 32768
+    t0 = time.time()
+    plain = config4_plain(nd)
+    packed, off, lens = _zlib_many(plain, 6, 0, threads)
+    t_fix = time.time() - t0
+    assert (((packed[off + 2] >> 1) & 3) == 2).all(), "config4 streams must start with a dynamic block"
+    stride = (int(lens.max()) + 15) & ~15
+    idx = np.arange(stride)[None, :]
+    comp = np.zeros((nd, stride), dtype=np.uint8)
+    mask = idx < lens[:, None]
+    comp[mask] = packed[(off[:, None] + idx)[mask]]
+    sel = torch.arange(n, device=dev) % nd
+    d_in = torch.from_numpy(comp).to(dev)[sel].contiguous()
+    d_len = torch.from_numpy(lens.astype(np.int32)).to(dev)[sel].contiguous()
+    d_plain = torch.from_numpy(plain).to(dev)
+    d_out = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    d_olen = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def run(flags=0):
+        eng.decompress_batch(d_in, None, stride, d_len, d_out, L, L, d_olen, d_st, n, flags=flags, stream=stream)
+    run(hz.F_VERIFY_ADLER)
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum()) == 0 and bool((d_olen == L).all()), "config4: status / length"
+    assert torch.equal(d_out.view(n, L), d_plain[sel]), "config4: output differs from the original"
+    ms, best = _time_launches(run, steps)
+    ms_v, _ = _time_launches(lambda: run(hz.F_VERIFY_ADLER), steps)
+    cbytes = int(d_len.sum(dtype=torch.int64))
+    alg = cbytes + n * L
+    return {"workload": "BASELINE configs[3]: %d x 32 KiB host-zlib level-6 dynamic-tree streams (drawn cyclically from "
+                        "%d distinct), OBSIZE = 32768, decompress-only" % (n, nd),
+            "decompress_gbps": n * L / (ms * 1e-3) / 1e9, "decompress_gbps_verified": n * L / (ms_v * 1e-3) / 1e9,
+            "ms": ms, "ms_best": best, "compressed_ratio": cbytes / (n * L), "byte_exact_vs_original": True,
+            "roofline": {"bound": "hbm", "kernel": "dynamic-Huffman route", "achieved": alg / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": alg, "traffic": ncu_traffic("config4", n)},
+            "fixture_seconds": t_fix}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -228,6 +397,9 @@ def main():
     ap.add_argument("--ref-blocks", type=int, default=1 << 16, help="blocks per step of the CPU arms")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[2] / [3] (decompress-only legs)")
+    ap.add_argument("--c4-streams", type=int, default=100000)
+    ap.add_argument("--c4-distinct", type=int, default=16384)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -322,6 +494,18 @@ def main():
     else:
         comp_bytes_all = comp_bytes
     t_total, t_c, t_d = [float(x) for x in times.tolist()]
+
+    # the same decompress pass with the container checksum verified (zlib's contract; the reference itself
+    # never checks it, deflate.py:1535), timed separately so both numbers stand side by side
+    def dec_verified():
+        eng.decompress_batch(d_comp, None, ostride, d_clen, d_back, BLOCK, BLOCK, d_blen, d_bst, n,
+                             flags=hz.F_VERIFY_ADLER, stream=stream)
+    t_dv, _ = _time_launches(dec_verified, max(3, args.steps // 2))
+    assert int(d_bst.abs().sum()) == 0
+    tdv = torch.tensor([t_dv], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tdv, op=dist.ReduceOp.MAX)
+    t_dv = float(tdv.item())
 
     gather = None
     if dist:
@@ -439,24 +623,38 @@ def main():
 
     if e2e:
         line["e2e"] = e2e
+    line["decompress_gbps_verified"] = unc / (t_dv * 1e-3) / 1e9
 
     # ---- cpu_baseline: the oracle port on the host cores, bounded sample, N = 1 only ----
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         ns = min(args.ref_blocks, n)
         sample = d_in.view(n, BLOCK)[:ns].cpu().numpy()
-        v, c, d, secs = cpu_roundtrip(sample, cores)
-        rep = max(1, int(20.0 / max(secs, 1e-3)))
+        r = cpu_roundtrip(sample, cores)
+        rep = max(1, int(20.0 / max(r["seconds"], 1e-3)))
         if rep > 1:
-            v, c, d, secs = cpu_roundtrip(sample, cores, repeat=min(rep, 128))
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            r = cpu_roundtrip(sample, cores, repeat=min(rep, 128))
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": r["kind"],
                                 "sample": "first %d blocks of the workload, %.1f s of CPU work, %d threads"
-                                          % (ns, secs, cores),
-                                "compress_gbps": c, "decompress_gbps": d}
+                                          % (ns, r["seconds"], cores),
+                                "compress_gbps": r["compress_gbps"], "decompress_gbps": r["decompress_gbps"],
+                                "port_inflate_gbps": r["port_inflate_gbps"], "zlib_inflate_gbps": r["zlib_inflate_gbps"],
+                                "what": "tuned C port of deflate.py's compressor (bit-identical output) + the faster of "
+                                        "port / host-zlib inflate"}
         try:
             line["cpu_zlib"] = dict(cpu_zlib(sample, cores), cores=cores)
         except Exception as e:      # informational only
             line["cpu_zlib"] = {"error": repr(e)}
+
+    if world == 1 and not args.no_configs:
+        del d_comp, d_back
+        torch.cuda.empty_cache()
+        threads = os.cpu_count() or 1
+        cfgs = {}
+        cfgs["config3"] = run_config3(eng, hz, d_in, n, dev, stream, max(3, args.steps // 2), threads, peak)
+        cfgs["config4"] = run_config4(eng, hz, args.c4_streams, min(args.c4_distinct, args.c4_streams), dev, stream,
+                                      max(3, args.steps // 2), threads, peak)
+        line["configs"] = cfgs
 
     print(json.dumps(line), flush=True)
     if dist:

@@ -67,13 +67,48 @@ static inline uint64_t host_chunk(uint64_t n, uint64_t bytes_per_item)
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int check_ctx(hdlz_ctx *ctx)
+static int check_ctx(hdlz_ctx *ctx, DeviceGuard &guard)
 {
     if (!ctx) return set_error(HDLZ_ERR_INVALID, "null context");
-    cudaError_t e = cudaSetDevice(ctx->device);
+    cudaError_t e = guard.enter(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     return HDLZ_SUCCESS;
 }
+
+// every entry point that touches the device: null check, make the context's device current until return
+#define HDLZ_ENTER(ctx)                  \
+    DeviceGuard guard__;                 \
+    int rc = check_ctx((ctx), guard__);  \
+    if (rc) return rc
+
+// lengths of a host batch, checked before anything is launched: a bad length would make a kernel read
+// past its slot (a sticky illegal-address error that kills the context)
+static int check_lengths(const uint32_t *len, uint64_t n, uint64_t stride, bool compress)
+{
+    if (!len) return HDLZ_SUCCESS;
+    for (uint64_t i = 0; i < n; i++) {
+        if (stride && len[i] > stride)
+            return set_error(HDLZ_ERR_INVALID, "in_len[%llu] = %u exceeds in_stride %llu", (unsigned long long)i, len[i],
+                             (unsigned long long)stride);
+        if (compress && len[i] >= (1u << HDLZ_LMAX))
+            return set_error(HDLZ_ERR_INVALID, "in_len[%llu] = %u does not fit LMAX", (unsigned long long)i, len[i]);
+    }
+    return HDLZ_SUCCESS;
+}
+
+// error exit of a chunked pipeline: nothing may still be copying into the caller's buffers
+static int drain(hdlz_ctx *ctx, int rc)
+{
+    for (int i = 0; i < 3; i++)
+        if (ctx->pipe[i]) cudaStreamSynchronize(ctx->pipe[i]);
+    return rc;
+}
+
+#define HDLZ_CUDA_DRAIN(ctx, call)                                   \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return drain((ctx), cuda_fail(e__, #call)); \
+    } while (0)
 
 }  // namespace hdlz
 
@@ -113,7 +148,8 @@ int hdlz_create(int device, hdlz_ctx **out)
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
     if (n == 0) return set_error(HDLZ_ERR_NODEVICE, "no CUDA device");
     if (device < 0 || device >= n) return set_error(HDLZ_ERR_INVALID, "device %d out of range (%d devices)", device, n);
-    HDLZ_CUDA(cudaSetDevice(device));
+    DeviceGuard guard;
+    HDLZ_CUDA(guard.enter(device));
     cudaDeviceProp prop;
     HDLZ_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
@@ -136,7 +172,8 @@ int hdlz_create(int device, hdlz_ctx **out)
 int hdlz_destroy(hdlz_ctx *c)
 {
     if (!c) return HDLZ_SUCCESS;
-    cudaSetDevice(c->device);
+    DeviceGuard guard;
+    guard.enter(c->device);
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
@@ -185,8 +222,7 @@ int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, 
                         uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
                         uint32_t *d_status, uint64_t n, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (n == 0) return HDLZ_SUCCESS;
     if (!d_in || !d_out || !d_out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if (!aligned16(d_in) || !aligned16(d_out) || (in_stride & 15) || (out_stride & 15))
@@ -201,8 +237,7 @@ int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
                           const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
                           uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (n == 0) return HDLZ_SUCCESS;
     if (!d_in || !d_in_len || !d_out || !d_out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if (out_cap > out_stride) return set_error(HDLZ_ERR_INVALID, "out_cap exceeds out_stride");
@@ -218,11 +253,11 @@ int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, con
                        uint32_t uniform_len, uint8_t *out, uint64_t out_stride, uint32_t *out_len,
                        uint32_t *status, uint64_t n)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (n == 0) return HDLZ_SUCCESS;
     if (!in || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if ((in_stride & 15) || (out_stride & 15)) return set_error(HDLZ_ERR_INVALID, "strides must be multiples of 16");
+    if ((rc = check_lengths(in_len, n, in_stride, true))) return rc;
     const size_t in_bytes = (size_t)n * in_stride, out_bytes = (size_t)n * out_stride;
     if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;
     if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_bytes))) return rc;
@@ -235,21 +270,21 @@ int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, con
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
         cudaStream_t s = ctx->pipe[k % 3];
-        HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
+        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                   cudaMemcpyHostToDevice, s));
         if (in_len)
-            HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         rc = hdlz_compress_batch(ctx, ctx->d_in + first * in_stride, in_stride, in_len ? d_len + first : nullptr,
                                  uniform_len, ctx->d_out + first * out_stride, out_stride, d_olen + first, d_st + first,
                                  m, s);
-        if (rc) return rc;
-        HDLZ_CUDA(cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
+        if (rc) return drain(ctx, rc);
+        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
                                   cudaMemcpyDeviceToHost, s));
-        HDLZ_CUDA(cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (status)
-            HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
+    for (int i = 0; i < 3; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
     return HDLZ_SUCCESS;
 }
 
@@ -257,11 +292,11 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
                          const uint32_t *in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
                          uint32_t *out_len, uint32_t *status, uint64_t n, uint32_t flags)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (n == 0) return HDLZ_SUCCESS;
     if (!in || !in_len || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if (out_cap > out_stride) return set_error(HDLZ_ERR_INVALID, "out_cap exceeds out_stride");
+    if (!in_off && (rc = check_lengths(in_len, n, in_stride, false))) return rc;
     size_t in_bytes;
     if (in_off) {
         in_bytes = 0;
@@ -295,32 +330,31 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
         if (in_off) {
             const uint64_t lo = (nchunks == 1 ? 0 : in_off[first]) & ~(uint64_t)15;
             const uint64_t hi = nchunks == 1 ? in_bytes : in_off[first + m - 1] + in_len[first + m - 1];
-            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, s));
-            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_off + first, in_off + first, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_off + first, in_off + first, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         } else {
-            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                       cudaMemcpyHostToDevice, s));
         }
-        HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off + first : nullptr,
                             in_stride, d_len + first, ctx->d_out + first * out_stride, out_stride, out_cap,
                             d_olen + first, d_st + first, m, flags, ctx->d_work + 2 * first + 32 * (uint64_t)k, k, s);
-        if (rc) return rc;
-        HDLZ_CUDA(cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
+        if (rc) return drain(ctx, rc);
+        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
                                   cudaMemcpyDeviceToHost, s));
-        HDLZ_CUDA(cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (status)
-            HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
+    for (int i = 0; i < 3; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
     return HDLZ_SUCCESS;
 }
 
 int hdlz_pack_batch(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
                     uint64_t *d_off, uint64_t *d_total, uint64_t n, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (n == 0) return HDLZ_SUCCESS;
     if (!d_slots || !d_len || !d_packed || !d_off || !d_total) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if ((reinterpret_cast<uintptr_t>(d_slots) & 3u) || (reinterpret_cast<uintptr_t>(d_packed) & 3u) || (stride & 3u))
@@ -332,12 +366,13 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
                               uint32_t uniform_len, uint8_t *out, uint64_t out_cap, uint64_t *out_off,
                               uint32_t *out_len, uint32_t *status, uint64_t n, uint64_t *out_total)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (out_total) *out_total = 0;
     if (n == 0) return HDLZ_SUCCESS;
     if (!in || !out || !out_off || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if (in_stride & 15) return set_error(HDLZ_ERR_INVALID, "in_stride must be a multiple of 16");
+    if ((rc = check_lengths(in_len, n, in_stride, true))) return rc;
+    if (!in_len && uniform_len > in_stride) return set_error(HDLZ_ERR_INVALID, "uniform_len exceeds in_stride");
     uint32_t maxlen = uniform_len;
     if (in_len) {
         maxlen = 0;
@@ -371,38 +406,38 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
         if (c < nchunks) {
             const uint64_t first = c * chunk, m = n - first < chunk ? n - first : chunk;
             cudaStream_t s = ctx->pipe[c % 3];
-            HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                       cudaMemcpyHostToDevice, s));
             if (in_len)
-                HDLZ_CUDA(cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             rc = hdlz_compress_batch(ctx, ctx->d_in + first * in_stride, in_stride, in_len ? d_len + first : nullptr,
                                      uniform_len, ctx->d_out + first * slot, slot, d_olen + first, d_st + first, m, s);
-            if (rc) return rc;
+            if (rc) return drain(ctx, rc);
             rc = launch_pack(ctx, ctx->d_out + first * slot, slot, d_olen + first, d_packed + first * slot, d_off + first,
                              d_tot + c, m, s);
-            if (rc) return rc;
-            HDLZ_CUDA(cudaMemcpyAsync(h_tot + c, d_tot + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            HDLZ_CUDA(cudaMemcpyAsync(out_off + first, d_off + first, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            HDLZ_CUDA(cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (rc) return drain(ctx, rc);
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(h_tot + c, d_tot + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_off + first, d_off + first, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             if (status)
-                HDLZ_CUDA(cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         }
         if (c >= 2) {
             const uint64_t cc = c - 2, first = cc * chunk, m = n - first < chunk ? n - first : chunk;
             cudaStream_t s = ctx->pipe[cc % 3];
-            HDLZ_CUDA(cudaStreamSynchronize(s));
+            HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
             const uint64_t tot = h_tot[cc];
             if (base + tot > out_cap) {
                 for (int i = 0; i < 3; i++) cudaStreamSynchronize(ctx->pipe[i]);
                 return set_error(HDLZ_ERR_INVALID, "packed output needs more than out_cap = %llu bytes",
                                  (unsigned long long)out_cap);
             }
-            HDLZ_CUDA(cudaMemcpyAsync(out + base, d_packed + first * slot, tot, cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + base, d_packed + first * slot, tot, cudaMemcpyDeviceToHost, s));
             for (uint64_t i = first; i < first + m; i++) out_off[i] += base;      // chunk-local -> global offsets
             base += tot;
         }
     }
-    for (int i = 0; i < 3; i++) HDLZ_CUDA(cudaStreamSynchronize(ctx->pipe[i]));
+    for (int i = 0; i < 3; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
     if (out_total) *out_total = base;
     return HDLZ_SUCCESS;
 }
@@ -410,8 +445,7 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
 int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
                          uint32_t *out_len, uint32_t *status)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (!in || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if (len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
     *out_len = 0;
@@ -442,8 +476,7 @@ int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t
 int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
                            uint32_t *out_len, uint32_t *status, uint32_t flags)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (!in || !out_len || (!out && out_cap)) return set_error(HDLZ_ERR_INVALID, "null buffer");
     *out_len = 0;
     const size_t out_slot = ((size_t)out_cap + 15) & ~(size_t)15;
@@ -470,8 +503,7 @@ int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8
 
 int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (!d_ptr) return set_error(HDLZ_ERR_INVALID, "null output pointer");
     HDLZ_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
     return HDLZ_SUCCESS;
@@ -479,16 +511,14 @@ int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr)
 
 int hdlz_dev_free(hdlz_ctx *ctx, void *d_ptr)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     HDLZ_CUDA(cudaFree(d_ptr));
     return HDLZ_SUCCESS;
 }
 
 int hdlz_host_alloc_pinned(hdlz_ctx *ctx, size_t bytes, void **h_ptr)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (!h_ptr) return set_error(HDLZ_ERR_INVALID, "null output pointer");
     HDLZ_CUDA(cudaMallocHost(h_ptr, bytes ? bytes : 16));
     return HDLZ_SUCCESS;
@@ -496,32 +526,28 @@ int hdlz_host_alloc_pinned(hdlz_ctx *ctx, size_t bytes, void **h_ptr)
 
 int hdlz_host_free_pinned(hdlz_ctx *ctx, void *h_ptr)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     HDLZ_CUDA(cudaFreeHost(h_ptr));
     return HDLZ_SUCCESS;
 }
 
 int hdlz_copy_h2d(hdlz_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     HDLZ_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return HDLZ_SUCCESS;
 }
 
 int hdlz_copy_d2h(hdlz_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     HDLZ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return HDLZ_SUCCESS;
 }
 
 int hdlz_stream_sync(hdlz_ctx *ctx, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     HDLZ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return HDLZ_SUCCESS;
 }
@@ -529,8 +555,7 @@ int hdlz_stream_sync(hdlz_ctx *ctx, void *stream)
 int hdlz_generate_blocks(hdlz_ctx *ctx, uint8_t *d_out, uint64_t stride, uint32_t len, uint64_t n, uint64_t seed,
                          uint64_t first_block, void *stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
+    HDLZ_ENTER(ctx);
     if (!d_out) return set_error(HDLZ_ERR_INVALID, "null buffer");
     if (len > stride) return set_error(HDLZ_ERR_INVALID, "len exceeds stride");
     return launch_generate(ctx, d_out, stride, len, n, seed, first_block, (cudaStream_t)stream);

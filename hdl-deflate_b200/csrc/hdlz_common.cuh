@@ -40,7 +40,33 @@ struct hdlz_ctx {
     cudaStream_t stream;  // owned, used by the host-buffer entry points
     cudaStream_t pipe[3];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls
     unsigned long long launches;
+    // per-context launch state (was function-static: two contexts / threads raced on it)
+    bool compress_attr_set;   // cudaFuncSetAttribute of k_compress done for this context's device
+    int l2_persist, l2_window, l2_carved;   // persisting-L2 limits of the device, and whether this context carved it
 };
+
+namespace hdlz {
+// Makes the context's device current for one entry point and restores the caller's device on return
+// (an engine on GPU k must not change the calling thread's current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int device)
+    {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev != device) {
+            e = cudaSetDevice(device);
+            switched = e == cudaSuccess;
+        }
+        return e;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+}  // namespace hdlz
 
 namespace hdlz {
 

@@ -460,14 +460,13 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
                     uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
                     uint32_t *d_status, uint64_t n, cudaStream_t s)
 {
-    static bool attr_set[64] = {false};
     if (n == 0) return HDLZ_SUCCESS;
-    if (!attr_set[ctx->device & 63]) {
+    if (!ctx->compress_attr_set) {
         HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set[ctx->device & 63] = true;
+        ctx->compress_attr_set = true;
     }
     uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
     const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;      // persistent: a multiple of the SM count

@@ -121,6 +121,7 @@ __device__ __noinline__ int lane_build(const uint8_t *lens, int nsym, uint16_t *
 {
     uint16_t first[16], offs[16], run[16];
     for (int l = 0; l < 16; ++l) { cnt[l] = 0; run[l] = 0; }
+    resume[0] = resume[1] = 0;      // a code without symbols must not leave the previous build's resume point behind
     for (int s = 0; s < nsym; ++s) cnt[lens[s]]++;
     uint32_t *t32 = reinterpret_cast<uint32_t *>(tbl);
     for (int i = 0; i < (1 << tbits) / 2; ++i) t32[i] = 0;
@@ -745,21 +746,19 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
         // as the device lets a window persist).  The carve-out is a device-wide limit and costs the
         // other kernels L2 capacity (the fixed-block kernel lost 10 % with 79 MB set aside), hence
         // opt-in, and given back by the next call without the flag.
-        static int l2_persist[64] = {0}, l2_window[64] = {0}, l2_carved[64] = {0};
-        const int dv = ctx->device & 63;
-        if (!l2_window[dv]) {
+        if (!ctx->l2_window) {
             int v = 0;
             cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-            l2_persist[dv] = v;
+            ctx->l2_persist = v;
             cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-            l2_window[dv] = v > 0 ? v : -1;
+            ctx->l2_window = v > 0 ? v : -1;
             (void)cudaGetLastError();
         }
-        const bool persist = (flags & HDLZ_F_PERSIST_TABLES) && l2_persist[dv] > 0 && l2_window[dv] > 0;
-        if (persist != (l2_carved[dv] != 0)) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist ? (size_t)l2_persist[dv] : 0);
+        const bool persist = (flags & HDLZ_F_PERSIST_TABLES) && ctx->l2_persist > 0 && ctx->l2_window > 0;
+        if (persist != (ctx->l2_carved != 0)) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist ? (size_t)ctx->l2_persist : 0);
             (void)cudaGetLastError();
-            l2_carved[dv] = persist ? 1 : 0;
+            ctx->l2_carved = persist ? 1 : 0;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)dyn_blocks);
@@ -769,11 +768,11 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
         cudaLaunchAttribute attr[1];
         unsigned nattr = 0;
         if (persist) {
-            const size_t win = hot_bytes < (size_t)l2_window[dv] ? hot_bytes : (size_t)l2_window[dv];
+            const size_t win = hot_bytes < (size_t)ctx->l2_window ? hot_bytes : (size_t)ctx->l2_window;
             attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
             attr[0].val.accessPolicyWindow.base_ptr = hot;
             attr[0].val.accessPolicyWindow.num_bytes = win;
-            attr[0].val.accessPolicyWindow.hitRatio = win <= (size_t)l2_persist[dv] ? 1.0f : (float)l2_persist[dv] / (float)win;
+            attr[0].val.accessPolicyWindow.hitRatio = win <= (size_t)ctx->l2_persist ? 1.0f : (float)ctx->l2_persist / (float)win;
             attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             nattr = 1;

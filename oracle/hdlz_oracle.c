@@ -15,7 +15,7 @@
  * The inflate restatement is checked against zlib, which is the reference's own
  * decompress check (test_deflate.py:194).
  *
- * Build: see oracle/Makefile (gcc -O2 -shared -fPIC ... -lz -lpthread).
+ * Build: see oracle/Makefile (gcc -O3 -shared -fPIC ... -lz -lpthread).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -150,6 +150,100 @@ int hdlz_oracle_compress_ex(const uint8_t *x, uint32_t L, uint8_t *out, uint32_t
 int hdlz_oracle_compress(const uint8_t *x, uint32_t L, uint8_t *out, uint32_t cap, uint32_t *out_len)
 {
     return hdlz_oracle_compress_ex(x, L, out, cap, out_len, 32, 10);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Tuned CPU arm of the same contract (the "fair" baseline of bench.py):     */
+/* identical bytes to hdlz_oracle_compress (tests/test_oracle.py checks it   */
+/* on the golden vectors and on fuzz), but written for speed — SSE2 byte     */
+/* compares stand in for the 32 matcher3 comparators (deflate.py:407-418),   */
+/* a 64-bit bit buffer for put/do_flush (:535-567), zlib's adler32 for the   */
+/* CSTATIC / CHECKSUM sums (:826-831, :884-897).  CWINDOW = 32 only.         */
+/* ------------------------------------------------------------------------ */
+#include <emmintrin.h>
+
+/* bit i <=> x[p - 32 + i] == x[p]  (distance 32 - i); needs p >= 32 */
+static inline uint32_t eq_mask32(const uint8_t *x, uint32_t p)
+{
+    const __m128i v = _mm_set1_epi8((char)x[p]);
+    const __m128i a = _mm_loadu_si128((const __m128i *)(x + p - 32));
+    const __m128i b = _mm_loadu_si128((const __m128i *)(x + p - 16));
+    return (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a, v)) |
+           ((uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(b, v)) << 16);
+}
+
+typedef struct { uint8_t *out; uint32_t cap, pos; uint64_t acc; unsigned fill; int ovf; } bitw64_t;
+
+static inline void bw64_put(bitw64_t *w, uint32_t v, unsigned n)     /* n <= 24, fill < 32 on entry */
+{
+    w->acc |= (uint64_t)v << w->fill;
+    w->fill += n;
+    if (w->fill >= 32) {
+        if (w->pos + 4 <= w->cap) memcpy(w->out + w->pos, &w->acc, 4); else w->ovf = 1;
+        w->pos += 4;
+        w->acc >>= 32;
+        w->fill -= 32;
+    }
+}
+
+int hdlz_oracle_compress_fast(const uint8_t *x, uint32_t L, uint8_t *out, uint32_t cap, uint32_t *out_len,
+                              unsigned maxlen)
+{
+    static uint32_t lit_tok[256], len_tok[11], dist_tok[33];     /* code | nbits << 16 */
+    static volatile int ready = 0;
+    if (!ready) {
+        for (unsigned s = 0; s < 256; s++) { unsigned c, n; fixed_code(s, &c, &n); lit_tok[s] = c | (n << 16); }
+        for (unsigned m = 3; m <= 10; m++) { unsigned c, n; fixed_code(254 + m, &c, &n); len_tok[m] = c | (n << 16); }
+        for (unsigned d = 1; d <= 32; d++) {
+            unsigned c = 0;
+            while (kCopyDistance[c + 1] <= d) c++;
+            unsigned eb = c < 2 ? 0 : (c >> 1) - 1;
+            dist_tok[d] = (rev_bits(c, 5) | ((d - kCopyDistance[c]) << 5)) | ((5 + eb) << 16);
+        }
+        __sync_synchronize();
+        ready = 1;
+    }
+    *out_len = 0;
+    if (L < 5) return ST_SHORT_INPUT;
+    bitw64_t w = {out, cap, 0, 0, 0, 0};
+    bw64_put(&w, 0x78 | (0x9C << 8) | (3u << 16), 19);
+    uint32_t p = 0;
+    while (p < L) {
+        unsigned d = 0, m = 1;
+        if (p >= 1 && p + 5 <= L) {
+            if (p >= 32) {
+                uint32_t m3 = eq_mask32(x, p) & eq_mask32(x, p + 1) & eq_mask32(x, p + 2);
+                if (m3) d = (unsigned)__builtin_clz(m3) + 1;       /* highest bit = nearest distance */
+            } else {
+                for (unsigned dd = 1; dd <= p; dd++)
+                    if (x[p - dd] == x[p] && x[p - dd + 1] == x[p + 1] && x[p - dd + 2] == x[p + 2]) { d = dd; break; }
+            }
+            if (d) {
+                m = 3;
+                while (m < maxlen && p + m + 3 <= L && x[p - d + m] == x[p + m]) m++;
+            }
+        }
+        if (d) {
+            bw64_put(&w, len_tok[m] & 0xFFFF, len_tok[m] >> 16);
+            bw64_put(&w, dist_tok[d] & 0xFFFF, dist_tok[d] >> 16);
+        } else {
+            bw64_put(&w, lit_tok[x[p]] & 0xFFFF, lit_tok[x[p]] >> 16);
+        }
+        p += m;
+    }
+    bw64_put(&w, 0, 7);
+    if (w.fill & 7) bw64_put(&w, 0, 8 - (w.fill & 7));
+    const uint32_t ad = (uint32_t)adler32(1L, x, L);
+    while (w.fill) {                                              /* whole bytes left in the buffer */
+        if (w.pos < w.cap) w.out[w.pos] = (uint8_t)w.acc; else w.ovf = 1;
+        w.pos++; w.acc >>= 8; w.fill -= 8;
+    }
+    for (int k = 3; k >= 0; k--) {
+        if (w.pos < w.cap) w.out[w.pos] = (uint8_t)(ad >> (8 * k)); else w.ovf = 1;
+        w.pos++;
+    }
+    *out_len = w.pos;
+    return w.ovf ? ST_OUT_OVERFLOW : ST_OK;
 }
 
 /* Token trace for debugging / structural tests: fills tok[i] = p | len<<24 | dist<<16. */
@@ -347,7 +441,7 @@ int hdlz_oracle_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32
 /* multi-threaded batch drivers (CPU baselines of bench.py)                  */
 /* ------------------------------------------------------------------------ */
 typedef struct {
-    int kind;                 /* 0 port-compress, 1 zlib deflate, 2 zlib inflate, 3 port-inflate */
+    int kind;                 /* 0 port-compress, 1 zlib deflate, 2 zlib inflate, 3 port-inflate, 4 tuned port-compress */
     const uint8_t *in; const uint64_t *in_off; const uint32_t *in_len;
     uint8_t *out; const uint64_t *out_off; uint32_t out_cap; uint32_t *out_len; uint32_t *status;
     uint64_t lo, hi; int level, strategy;
@@ -365,6 +459,8 @@ static void *worker(void *arg)
         int st = 0;
         if (j->kind == 0) {
             st = hdlz_oracle_compress(src, j->in_len[i], dst, j->out_cap, &n);
+        } else if (j->kind == 4) {
+            st = hdlz_oracle_compress_fast(src, j->in_len[i], dst, j->out_cap, &n, 10);
         } else if (j->kind == 3) {
             st = hdlz_oracle_inflate(src, j->in_len[i], dst, j->out_cap, &n, 0);
         } else if (j->kind == 1) {

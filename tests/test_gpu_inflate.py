@@ -228,3 +228,66 @@ def test_corrupted_streams_never_crash(engine):
             assert want is not None and out[i, :out_len[i]].tobytes() == want, i
         else:
             assert want is None or len(want) > 2 * len(data), (i, status[i])
+
+
+class _Bits(object):
+    """LSB-first bit writer for hand-made deflate blocks."""
+
+    def __init__(self):
+        self.v, self.n = 0, 0
+
+    def put(self, val, nbits):
+        self.v |= val << self.n
+        self.n += nbits
+
+    def code(self, c, nbits):                   # Huffman codes go MSB-first
+        self.put(int(format(c, "0%db" % nbits)[::-1], 2), nbits)
+
+    def bytes(self):
+        return self.v.to_bytes((self.n + 7) // 8, "little")
+
+
+def _length_symbol_with_empty_distance_code():
+    """Dynamic block whose distance code has no symbols at all (legal for literal-only blocks) but
+    which then uses length symbol 257: zlib says 'invalid distance code'."""
+    b = _Bits()
+    b.put(1, 1); b.put(2, 2)                    # BFINAL, BTYPE = 2
+    b.put(1, 5); b.put(0, 5); b.put(12, 4)      # HLIT = 258, HDIST = 1, HCLEN = 16
+    cl = {0: 2, 2: 2, 17: 2, 18: 2}
+    for s in (16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2):
+        b.put(cl.get(s, 0), 3)
+    clcode = {0: 0, 2: 1, 17: 2, 18: 3}
+    def zeros(n):
+        b.code(clcode[18], 2); b.put(n - 11, 7)
+    zeros(97)
+    b.code(clcode[2], 2); b.code(clcode[2], 2)          # 'a', 'b'
+    zeros(138); zeros(19)
+    b.code(clcode[2], 2); b.code(clcode[2], 2)          # 256, 257
+    b.code(clcode[0], 2)                                # the one distance length: 0
+    lit = {97: 0, 98: 1, 256: 2, 257: 3}
+    b.code(lit[97], 2)
+    b.code(lit[257], 2)                                 # length 3 ... and no distance code exists
+    b.put(0, 16)
+    b.code(lit[256], 2)
+    body = b.bytes()
+    return b"\x78\x9c" + body + zlib.adler32(b"aaaa").to_bytes(4, "big")
+
+
+@pytest.mark.parametrize("flags", [0, 3])
+def test_empty_distance_code_is_rejected_on_every_route(engine, flags):
+    """A code without symbols must not be decoded with the previous table's resume point
+    (round-1 advisor finding): all routes and zlib reject the stream, with and without checksums."""
+    bad = _length_symbol_with_empty_distance_code()
+    with pytest.raises(zlib.error):
+        zlib.decompress(bad)
+    good = zl(bytes(np.random.default_rng(1).integers(97, 101, 3000, dtype=np.uint8)), 6)   # builds real tables first
+    n = 1100
+    streams = [good if i % 2 == 0 else bad for i in range(n)]
+    stride = (max(len(s) for s in streams) + 15) & ~15
+    buf = np.zeros((n, stride), dtype=np.uint8)
+    for i, s in enumerate(streams):
+        buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    lens = np.array([len(s) for s in streams], dtype=np.uint32)
+    for route in (0, FORCE_GENERAL, FORCE_LANES):
+        out, out_len, status = engine.decompress_host(buf, lens, 4096, flags=flags | route)
+        assert (status[0::2] == 0).all() and (status[1::2] == 3).all(), (route, status[:8])

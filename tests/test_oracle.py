@@ -40,6 +40,26 @@ def test_compress_restatement_matches_golden_match5():
     assert differs > 10            # the switch changes the streams
 
 
+def test_tuned_cpu_arm_equals_the_restatement():
+    """hdlz_oracle_compress_fast (the CPU baseline bench.py times) must produce the restatement's bytes:
+    golden vectors of both MATCH10 settings plus seeded fuzz around the 32-byte window edge."""
+    from hdl_deflate_b200 import workload
+    for name, ml in (("compress_golden.json", 10), ("compress_golden_match5.json", 5)):
+        for c in load_golden(name):
+            data = golden_input(c)
+            st, out = hdlz_oracle.compress_fast(data, ml)
+            assert st == 0 and hashlib.sha256(out).hexdigest() == c["out_sha256"], c["name"]
+    rnd = random.Random(5)
+    for t in range(1500):
+        n = rnd.choice([5, 6, 31, 32, 33, 34, 35, 36, 64, 65, 300, 2047, 2048, 4100])
+        d = [bytes(rnd.randrange(256) for _ in range(n)), bytes(rnd.choice(b"ab") for _ in range(n)),
+             workload.block(t, n), bytes([rnd.randrange(256)]) * n][t % 4]
+        for ml in (10, 5):
+            assert hdlz_oracle.compress_fast(d, ml) == hdlz_oracle.compress(d, 32, ml), (t, n, ml)
+    for n in range(5):
+        assert hdlz_oracle.compress_fast(bytes(n)) == (1, b"")
+
+
 def test_survey_known_answers():
     # SURVEY.md 8(a): vectors produced by the reference FSM
     assert hdlz_oracle.compress(b"abcde")[1].hex() == "789c4b4c4a4e49050005c801f0"

@@ -28,10 +28,23 @@ def _worker(rank, world, port, n_total, q):
         s = hdlz_oracle.compress(workload.block(i, 2048))[1]
         out[i - first, :len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8)
         lens[i - first] = len(s)
+    # pack the shard the way hdlz_pack_batch does: stream starts rounded up to 4, in block order
+    padded = (lens.to(torch.int64) + 3) & ~3
+    loff = torch.cumsum(padded, 0) - padded
+    packed = torch.zeros(int(padded.sum()) + 16, dtype=torch.uint8)
+    for i in range(last - first):
+        packed[int(loff[i]):int(loff[i]) + int(lens[i])] = out[i, :int(lens[i])]
+    # the input side: rank 0 owns all blocks, every rank receives its shard
+    blocks = torch.zeros((n_total, 2048), dtype=torch.uint8)
+    if rank == 0:
+        for i in range(n_total):
+            blocks[i] = torch.frombuffer(bytearray(workload.block(i, 2048)), dtype=torch.uint8)
+    mine = sharding.broadcast_blocks(blocks, src=0)
+    assert mine.shape[0] == last - first and mine[0].numpy().tobytes() == workload.block(first, 2048)
     all_len = sharding.gather_lengths(lens, n_total)
     off, total = sharding.packed_offsets(all_len)
-    gathered, all_len2 = sharding.gather_streams(out, lens, stride, n_total, dst=0)
-    assert torch.equal(all_len, all_len2)
+    gathered, off2, all_len2 = sharding.gather_streams(packed, lens, n_total, dst=0)
+    assert torch.equal(all_len, all_len2) and torch.equal(off, off2)
     if rank == 0:
         q.put((all_len.numpy(), off.numpy(), total, gathered.numpy()))
     dist.barrier()
@@ -68,8 +81,9 @@ def test_two_rank_gather_equals_single_process():
         assert p.exitcode == 0
     want = [hdlz_oracle.compress(workload.block(i, 2048))[1] for i in range(n_total)]
     assert list(all_len) == [len(s) for s in want]
-    assert total == sum(len(s) for s in want)
-    assert list(off) == list(np.cumsum([0] + [len(s) for s in want[:-1]]))
+    r4 = [(len(s) + 3) & ~3 for s in want]
+    assert total == sum(r4) == gathered.shape[0]          # packed: only stream bytes (starts 4-byte aligned)
+    assert list(off) == list(np.cumsum([0] + r4[:-1]))
     for i, s in enumerate(want):
-        assert gathered[i, :len(s)].tobytes() == s
-    assert gathered.shape == (n_total, compress_bound(2048))
+        assert gathered[int(off[i]):int(off[i]) + len(s)].tobytes() == s
+    assert total < 0.7 * n_total * compress_bound(2048)   # far less than the fixed slots
