@@ -29,7 +29,10 @@ int cuda_fail(cudaError_t e, const char *what)
     return set_error(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
-static int grow(void **p, size_t *cap, size_t need)
+int grow_device(void **p, size_t *cap, size_t need);
+static int grow(void **p, size_t *cap, size_t need) { return grow_device(p, cap, need); }
+
+int grow_device(void **p, size_t *cap, size_t need)
 {
     if (need <= *cap) return HDLZ_SUCCESS;
     if (*p) cudaFree(*p);
@@ -184,7 +187,13 @@ int hdlz_destroy(hdlz_ctx *c)
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->d_off) cudaFree(c->d_off);
-    if (c->d_work) cudaFree(c->d_work);
+    for (int i = 0; i < 3; i++) {
+        if (c->d_workb[i]) cudaFree(c->d_workb[i]);
+        if (c->d_split[i]) cudaFree(c->d_split[i]);
+        if (c->d_split_scratch[i]) cudaFree(c->d_split_scratch[i]);
+        if (c->slot_event[i]) cudaEventDestroy(c->slot_event[i]);
+    }
+    if (c->h_dyn_seen) cudaFreeHost(c->h_dyn_seen);
     if (c->d_queue) cudaFree(c->d_queue);
     if (c->d_pack) cudaFree(c->d_pack);
     for (int i = 0; i < 3; i++)
@@ -243,10 +252,8 @@ int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
     if (out_cap > out_stride) return set_error(HDLZ_ERR_INVALID, "out_cap exceeds out_stride");
     if ((reinterpret_cast<uintptr_t>(d_in) & 3u))
         return set_error(HDLZ_ERR_INVALID, "d_in must be 4-byte aligned");
-    // hand-over list of the lane kernel: context-owned, so one decompress call per context at a time
-    if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, inflate_work_words(n) * sizeof(uint32_t)))) return rc;
     return launch_inflate(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n,
-                          flags, ctx->d_work, 0, (cudaStream_t)stream);
+                          flags, 0, (cudaStream_t)stream);
 }
 
 int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
@@ -321,8 +328,7 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
         for (uint64_t i = 1; i < n && ascending; i++) ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1];
     const uint64_t chunk = (in_off && !ascending) ? n : host_chunk(n, (in_off ? in_bytes / n + 1 : in_stride) + out_stride);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
-    if ((rc = grow((void **)&ctx->d_work, &ctx->d_work_cap, (inflate_work_words(n) + 32 * nchunks + 32) * sizeof(uint32_t))))
-        return rc;
+    (void)nchunks;
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
@@ -339,7 +345,7 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
         HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off + first : nullptr,
                             in_stride, d_len + first, ctx->d_out + first * out_stride, out_stride, out_cap,
-                            d_olen + first, d_st + first, m, flags, ctx->d_work + 2 * first + 32 * (uint64_t)k, k, s);
+                            d_olen + first, d_st + first, m, flags, k % 3, s);
         if (rc) return drain(ctx, rc);
         HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
                                   cudaMemcpyDeviceToHost, s));

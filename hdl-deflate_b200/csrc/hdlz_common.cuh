@@ -12,6 +12,7 @@
 #define HDLZ_F_FORCE_LANES 0x200u     /* lane-per-stream kernel first, whatever the batch size */
 #define HDLZ_F_PERSISTENT_LANES 0x800u /* fixed/stored lane kernel as a persistent grid (experiment) */
 #define HDLZ_F_NO_LANE_SCRATCH 0x400u /* lanes hand dynamic-block streams to the warp-per-stream kernel */
+#define HDLZ_F_NO_SPLIT 0x1000u       /* dynamic-block streams stay on the lane-per-stream kernel (no two-phase route) */
 
 struct hdlz_ctx {
     int device;
@@ -35,8 +36,19 @@ struct hdlz_ctx {
     size_t h_small_cap;
     unsigned long long *d_queue;  // work-queue heads of the persistent compress grid, one slot per launch (ring)
     unsigned queue_seq;
-    uint32_t *d_work;  // [0] count, [4..] stream ids handed from the lane kernel to the warp kernel
-    size_t d_work_cap;
+    // inflate launches use one of three slots (the *_host pipelines keep three chunks in flight; the batch
+    // entry point uses slot 0).  Everything a launch shares with its kernels lives in its slot, and a slot's
+    // next launch waits for the event its previous launch recorded: two batches in flight never share
+    // hand-over lists, lane scratch or token pools.
+    uint32_t *d_workb[3];  // [0] count for the warp kernel, [1] dynamic-block count, [2..3] queue heads of the two-phase
+                           // route, [16..] stream ids handed over by the lane kernel (two lists of n)
+    size_t d_workb_cap[3];
+    cudaEvent_t slot_event[3];
+    void *d_split[3];      // token pool of the two-phase dynamic-block route (records | tokens | literals)
+    size_t d_split_cap[3];
+    void *d_split_scratch[3];
+    uint32_t *h_dyn_seen;  // pinned [3]: dynamic-block streams the slot's last launch saw -> sizes the pool of the next one
+    bool split_attr_set;
     cudaStream_t stream;  // owned, used by the host-buffer entry points
     cudaStream_t pipe[3];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls
     unsigned long long launches;
@@ -86,10 +98,8 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
                     uint32_t *d_status, uint64_t n, cudaStream_t s);
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
-                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, uint32_t *d_work,
-                   int lane_slot, cudaStream_t s);
-// words of device scratch launch_inflate needs for n streams (hand-over list of the lane kernel)
-inline size_t inflate_work_words(uint64_t n) { return 2 * (size_t)n + 16; }
+                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, int slot, cudaStream_t s);
+int grow_device(void **p, size_t *cap, size_t need);
 int launch_pack(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
                 uint64_t *d_off, uint64_t *d_total, uint64_t n, cudaStream_t s);
 int launch_gzip_trailers(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,

@@ -30,6 +30,7 @@
 
 #include "hdlz_common.cuh"
 #include "hdlz_frame.cuh"
+#include "hdlz_split.cuh"
 
 namespace hdlz {
 
@@ -188,10 +189,11 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, uint32_t flags,
                 uint32_t *__restrict__ work_list, uint32_t *__restrict__ work_count,
                 uint32_t *__restrict__ dyn_list, uint32_t *__restrict__ dyn_count,
-                const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, LaneScratch *scratch,
-                LaneHot *hot_base)
+                const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, uint32_t item_skip,
+                LaneScratch *scratch, LaneHot *hot_base)
 {
-    const uint64_t n_items = items ? (uint64_t)*item_count : n_streams;
+    // with a list, the first `item_skip` entries belong to another kernel (the two-phase route)
+    const uint64_t n_items = items ? (uint64_t)(*item_count > item_skip ? *item_count - item_skip : 0u) : n_streams;
     if (n_items == 0) return;
     __shared__ uint32_t s_lit[512];       // fixed tree: 9 stream bits -> entry (see fixed_lit_entry)
     __shared__ uint32_t s_dist[32];       // fixed tree: 5 stream bits -> distance entry
@@ -381,7 +383,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             if (next_item >= n_items) {
                 state = S_DONE;
             } else {
-                sid = items ? (uint64_t)items[next_item] : next_item;
+                sid = items ? (uint64_t)items[next_item + item_skip] : next_item;
                 next_item += n_threads;
                 to_dyn = false;
                 n_in = in_len[sid];
@@ -699,28 +701,36 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
-                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, uint32_t *d_work,
-                   int lane_slot, cudaStream_t s)
+                   uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, int slot, cudaStream_t s)
 {
     if (n == 0) return HDLZ_SUCCESS;
     // Few streams: one warp each is the better mapping.  Many streams: one lane each first,
     // the warp-per-stream kernel then finishes whatever was handed over.
     const bool lanes_first = !(flags & HDLZ_F_FORCE_GENERAL) && (n >= 1024 || (flags & HDLZ_F_FORCE_LANES)) &&
-                             n < 0xFFFFFFFFull && d_work != nullptr;
+                             n < 0xFFFFFFFFull;
     if (!lanes_first)
         return launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
                                       d_status, n, flags, nullptr, nullptr, s);
+    slot %= 3;
+    // everything this launch shares with its kernels lives in its slot; the slot's previous launch (any
+    // stream) must have finished with it
+    if (!ctx->slot_event[slot]) HDLZ_CUDA(cudaEventCreateWithFlags(&ctx->slot_event[slot], cudaEventDisableTiming));
+    else HDLZ_CUDA(cudaStreamWaitEvent(s, ctx->slot_event[slot], 0));
+    {
+        const int rc = grow_device((void **)&ctx->d_workb[slot], &ctx->d_workb_cap[slot], (2 * (size_t)n + 16) * sizeof(uint32_t));
+        if (rc) return rc;
+    }
     // d_work: [0] count of streams for the warp-per-stream kernel, [1] count of streams with dynamic
-    // blocks, [16 ..) the two lists (n entries each)
+    // blocks, [2..3] queue heads of the two-phase route, [16 ..) the two lists (n entries each)
+    uint32_t *d_work = ctx->d_workb[slot];
     uint32_t *count = d_work, *dyn_count = d_work + 1, *list = d_work + 16, *dyn_list = d_work + 16 + n;
-    HDLZ_CUDA(cudaMemsetAsync(d_work, 0, 2 * sizeof(uint32_t), s));
+    HDLZ_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(uint32_t), s));
     uint64_t blocks = (n + kLWarps * 32 - 1) / (kLWarps * 32);
     if (flags & HDLZ_F_PERSISTENT_LANES) {
         const uint64_t resident = (uint64_t)ctx->sm_count * kLaneCtasPerSm;
         if (blocks > resident) blocks = resident;
     }
-    // scratch for dynamic blocks: one slot per concurrent launch (the *_host pipelines run three)
-    const int slot = lane_slot % 3;
+    // scratch of the lane-per-stream dynamic-block kernel: per-thread tables in global memory
     const uint64_t dyn_blocks = (uint64_t)ctx->sm_count * kDynCtasPerSm;
     const size_t dyn_threads = (size_t)dyn_blocks * (kLWarps * 32);
     const size_t hot_bytes = dyn_threads * sizeof(LaneHot);
@@ -737,10 +747,58 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
     LaneScratch *scratch = have ? reinterpret_cast<LaneScratch *>(static_cast<uint8_t *>(ctx->d_lane[slot]) + hot_bytes) : nullptr;
     k_inflate_lanes<false><<<(unsigned)blocks, kLWarps * 32, 0, s>>>(
         d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len, d_status, n, flags, list, count,
-        scratch ? dyn_list : nullptr, dyn_count, nullptr, nullptr, nullptr, nullptr);
+        scratch ? dyn_list : nullptr, dyn_count, nullptr, nullptr, 0u, nullptr, nullptr);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     if (scratch) {
+        // ---- dynamic-block streams.  Two-phase route (hdlz_inflate_split.cu) for as many of them as its token pool
+        // holds; the pool follows the demand the slot's previous launch reported (a batch's dynamic-block count is
+        // only known on the device), starting from 256 MiB.
+        uint32_t split_items = 0;
+        const bool split_ok = !(flags & HDLZ_F_NO_SPLIT) && out_cap <= kSplitMaxOut && out_cap >= 16 &&
+                              !((flags & HDLZ_F_GZIP) && (flags & HDLZ_F_VERIFY_ADLER));
+        if (split_ok) {
+            if (!ctx->h_dyn_seen) {
+                if (cudaMallocHost((void **)&ctx->h_dyn_seen, 4 * sizeof(uint32_t)) == cudaSuccess)
+                    ctx->h_dyn_seen[0] = ctx->h_dyn_seen[1] = ctx->h_dyn_seen[2] = 0;
+                else (void)cudaGetLastError();
+            }
+            const size_t per = split_slot_bytes(out_cap);
+            uint64_t want = (256ull << 20) / per + 1;
+            if (ctx->h_dyn_seen && ctx->h_dyn_seen[slot] > want) want = ctx->h_dyn_seen[slot];
+            if (want > n) want = n;
+            if (ctx->d_split_cap[slot] / per < want) {
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                const size_t budget = (free_b + ctx->d_split_cap[slot]) / 2;          // never more than half of what is free
+                if (want * per > budget) want = budget / per;
+                if (ctx->d_split_cap[slot] / per < want) {
+                    if (ctx->d_split[slot]) HDLZ_CUDA(cudaFree(ctx->d_split[slot]));
+                    ctx->d_split[slot] = nullptr;
+                    ctx->d_split_cap[slot] = 0;
+                    if (cudaMalloc(&ctx->d_split[slot], want * per) == cudaSuccess) ctx->d_split_cap[slot] = want * per;
+                    else (void)cudaGetLastError();
+                }
+            }
+            if (!ctx->d_split_scratch[slot]) {
+                if (cudaMalloc(&ctx->d_split_scratch[slot], split_scratch_bytes(ctx)) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    ctx->d_split_scratch[slot] = nullptr;
+                }
+            }
+            if (ctx->d_split[slot] && ctx->d_split_scratch[slot]) {
+                const uint64_t fit = ctx->d_split_cap[slot] / per;
+                split_items = (uint32_t)(fit < n ? fit : n);
+                const int rc = launch_inflate_split(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap,
+                                                    d_out_len, d_status, flags, dyn_list, dyn_count, split_items,
+                                                    ctx->d_split[slot], ctx->d_split_scratch[slot], d_work + 2, s);
+                if (rc) return rc;
+            }
+            if (ctx->h_dyn_seen)
+                HDLZ_CUDA(cudaMemcpyAsync(ctx->h_dyn_seen + slot, dyn_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        }
+        // ---- what the pool did not hold (or the route does not take): the lane-per-stream kernel with per-lane
+        // tables in global memory.
         // the primary tables are re-read for every symbol while inputs and outputs stream through the L2
         // once.  With HDLZ_F_PERSIST_TABLES the launch asks the L2 to keep the table range (as much of it
         // as the device lets a window persist).  The carve-out is a device-wide limit and costs the
@@ -754,7 +812,7 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
             ctx->l2_window = v > 0 ? v : -1;
             (void)cudaGetLastError();
         }
-        const bool persist = (flags & HDLZ_F_PERSIST_TABLES) && ctx->l2_persist > 0 && ctx->l2_window > 0;
+        const bool persist = (flags & HDLZ_F_PERSIST_TABLES) && !split_items && ctx->l2_persist > 0 && ctx->l2_window > 0;
         if (persist != (ctx->l2_carved != 0)) {
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist ? (size_t)ctx->l2_persist : 0);
             (void)cudaGetLastError();
@@ -779,17 +837,18 @@ int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
         }
         cfg.attrs = attr;
         cfg.numAttrs = nattr;
-        const uint32_t *no_list = nullptr;
         uint32_t *no_out = nullptr;
         HDLZ_CUDA(cudaLaunchKernelEx(&cfg, k_inflate_lanes<true>, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride,
                                      out_cap, d_out_len, d_status, n, flags, list, count, no_out, no_out,
-                                     (const uint32_t *)dyn_list, (const uint32_t *)dyn_count, scratch, hot));
+                                     (const uint32_t *)dyn_list, (const uint32_t *)dyn_count, split_items, scratch, hot));
         ctx->launches++;
         HDLZ_CUDA(cudaGetLastError());
-        (void)no_list;
     }
-    return launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
-                                  d_status, n, flags, list, count, s);
+    const int rc = launch_inflate_general(ctx, d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap, d_out_len,
+                                          d_status, n, flags, list, count, s);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaEventRecord(ctx->slot_event[slot], s));
+    return HDLZ_SUCCESS;
 }
 
 }  // namespace hdlz

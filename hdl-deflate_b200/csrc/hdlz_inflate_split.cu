@@ -1,0 +1,659 @@
+// hdlz_inflate_split.cu — two-phase inflater for batches of dynamic-Huffman streams (zlib level 6,
+// BASELINE config 4: 100 000 x 32 KiB, OBSIZE = 32768).  Replaces the reference's decode states
+// BL / READBL / REPEAT / HF1..HF4 / NEXT / INFLATE / D_NEXT (deflate.py:1084-1517) and COPY
+// (:1593-1659) — split where the FSM interleaves them:
+//
+//   phase 1  k_decode_tokens   one THREAD per stream, decode only.  Symbol decode is serial per stream, so
+//            the batch parallelism is across streams; with no window access in this phase a lane never
+//            waits for a far back-reference, and its tables are small enough to live in shared memory:
+//            an 8-bit literal/length and a 7-bit distance primary table plus the two count arrays of the
+//            canonical code (832 B per lane, interleaved by lane: a bank serves two lanes).
+//            Longer codes (under 1 % of the symbols of level-6 streams) take a canonical bit-serial
+//            decode that resumes after the table's bits.  Output: a compact token stream in global
+//            memory — literal bytes, and one 32-bit token per copy
+//                bits 0..7 literals before the copy | 8..16 copy length (0 = none) | 17..31 distance - 1.
+//   phase 2  k_resolve_tokens  one WARP per stream, the stream's whole output (<= 32 KiB) staged in
+//            shared memory.  32 tokens per step: one packed warp scan gives every token its literal
+//            source and its output position, the lanes place their literals and then their copies —
+//            a copy runs as soon as its source lies below the first unresolved copy of the step
+//            (almost always at once: level-6 distances are far); copies longer than 32 bytes are done
+//            by the whole warp.  The finished window goes to HBM with coalesced 128-bit stores, and
+//            the optional Adler-32 is taken from the same 128-bit reads.
+//
+// Algorithmic HBM traffic per stream: C bytes read + L bytes written; the token stream adds its
+// own write + read (about 0.8 L on level-6 data).
+//
+// Streams this route does not take (out_cap > 32 KiB, gzip CRC check, pool exhausted) stay on the
+// lane-per-stream kernel of hdlz_inflate_lanes.cu.
+
+#include "hdlz_common.cuh"
+#include "hdlz_frame.cuh"
+#include "hdlz_split.cuh"
+
+namespace hdlz {
+namespace {
+
+constexpr int kDecWarps = 4;
+constexpr int kDecCtasPerSm = 2;
+constexpr int kLitBits = 8;
+constexpr int kDistBits = 7;
+// per-lane table block, in 16-bit entries
+constexpr int kLitEnt0 = 0;                                   // 256 entries
+constexpr int kDistEnt0 = kLitEnt0 + (1 << kLitBits);         // 128 entries (also the 7-bit code-length-code table)
+constexpr int kCntLEnt0 = kDistEnt0 + (1 << kDistBits);       // 16 codes per length, literal/length code
+constexpr int kCntDEnt0 = kCntLEnt0 + 16;                     // 16, distance code (and the code-length code)
+constexpr int kTabEntries = kCntDEnt0 + 16;                   // 416 entries = 832 B per lane
+
+constexpr int kResWarps = 2;
+constexpr int kResCtasPerSm = 3;
+constexpr int kWinBytes = (int)kSplitMaxOut + 16;             // the output of one stream + a zeroed tail to 16 bytes
+
+__constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+__constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35,
+                                      43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_lextra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2,
+                                     3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193,
+                                      257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193,
+                                      12289, 16385, 24577};
+
+// 16-bit arrays of one lane inside the warp's table block: entry i of lane l sits at byte i * 64 + 2 * l
+// (one multiply-add to address; a bank serves two lanes, so a look-up costs at most two wavefronts)
+struct LaneTab {
+    uint8_t *base;         // warp block + 2 * lane
+    __device__ __forceinline__ uint32_t get(int ent0, uint32_t idx) const
+    {
+        return *reinterpret_cast<const uint16_t *>(base + (size_t)(ent0 + idx) * 64u);
+    }
+    __device__ __forceinline__ void set(int ent0, uint32_t idx, uint32_t v) const
+    {
+        *reinterpret_cast<uint16_t *>(base + (size_t)(ent0 + idx) * 64u) = (uint16_t)v;
+    }
+};
+
+constexpr uint32_t kLongCode = 0xF000u;     // table entry of a code longer than the table: not a literal, length 0
+
+// Canonical Huffman tables of one code (HF1INIT..HF4, SPREAD; deflate.py:1227-1400), built by ONE thread:
+// primary table (symbol << 4 | length; kLongCode = longer code, also what an unused index holds) and count
+// array in its shared-memory block, sorted symbols and the resume point of the bit-serial decode in its
+// global scratch.  Returns 0, or 1 for an over-subscribed / illegally incomplete code (zlib's inflate_table rules).
+__device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t, int tent0, int tbits, int cent0,
+                                        uint16_t *sorted, uint16_t *resume, bool allow_incomplete)
+{
+    uint16_t cnt[16], first[16], offs[16], run[16];
+    for (int l = 0; l < 16; ++l) { cnt[l] = 0; run[l] = 0; }
+    for (int s = 0; s < nsym; ++s) cnt[lens[s]]++;
+    cnt[0] = 0;
+    for (int l = 0; l < 16; ++l) t.set(cent0, l, cnt[l]);
+    for (int i = 0; i < (1 << tbits); ++i) t.set(tent0, i, kLongCode);
+    resume[0] = resume[1] = 0;
+    int left = 1, maxlen = 0;
+    for (int l = 1; l <= 15; ++l) {
+        const int c = cnt[l];
+        left = 2 * left - c;
+        if (c) maxlen = l;
+        if (left < 0) return 1;
+    }
+    if (maxlen == 0) return 0;                 // no codes: any use fails later
+    if (left > 0 && !(allow_incomplete && maxlen == 1)) return 1;
+    uint32_t code = 0, off = 0;
+    for (int l = 1; l <= 15; ++l) {
+        first[l] = (uint16_t)code;
+        offs[l] = (uint16_t)off;
+        code = (code + cnt[l]) << 1;
+        off += cnt[l];
+    }
+    resume[0] = tbits < 15 ? first[tbits + 1] : 0;
+    resume[1] = tbits < 15 ? offs[tbits + 1] : 0;
+    for (int s = 0; s < nsym; ++s) {
+        const uint32_t l = lens[s];
+        if (!l) continue;
+        const uint32_t k = run[l]++;
+        sorted[offs[l] + k] = (uint16_t)s;
+        if ((int)l <= tbits) {
+            const uint32_t rev = __brev(first[l] + k) >> (32 - l);
+            const uint32_t ent = ((uint32_t)s << 4) | l;
+            for (uint32_t idx = rev; idx < (1u << tbits); idx += 1u << l) t.set(tent0, idx, ent);
+        }
+    }
+    return 0;
+}
+
+// code longer than the primary table: canonical decode one bit at a time, starting after the `tbits`
+// bits the table has already ruled out.  -> (sym << 4) | len, 0 = invalid
+__device__ __forceinline__ uint32_t split_slow(uint32_t bits, LaneTab t, int cent0, const uint16_t *sorted, int tbits,
+                                               const uint16_t *resume)
+{
+    int code = (int)((__brev(bits) >> (32 - tbits)) << 1), first = resume[0], index = resume[1];
+    for (int l = tbits + 1; l <= 15; ++l) {
+        code |= (int)((bits >> (l - 1)) & 1u);
+        const int c = (int)t.get(cent0, l);
+        if (code - c < first) return ((uint32_t)sorted[index + (code - first)] << 4) | (uint32_t)l;
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return 0;
+}
+
+// literal/length symbol 257..285 -> extra bits (0..5) | base length << 16
+__device__ __forceinline__ uint32_t len_entry(uint32_t sym) { return (uint32_t)c_lextra[sym - 257] | ((uint32_t)c_lbase[sym - 257] << 16); }
+// distance symbol 0..29 -> extra bits (0..13) | base distance << 8
+__device__ __forceinline__ uint32_t dist_entry(uint32_t d) { return (d < 2 ? 0u : (d >> 1) - 1u) | ((uint32_t)c_dbase[d] << 8); }
+
+// ---------------------------------------------------------------------------------------------------
+// phase 1: Huffman decode -> token stream
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDecWarps * 32, kDecCtasPerSm)
+k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint64_t in_stride,
+                const uint32_t *__restrict__ in_len, uint32_t out_cap, uint32_t flags,
+                const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, uint32_t max_items,
+                SplitScratch *scratch, uint32_t *tokbuf, uint32_t tokcap, uint32_t *litbuf, uint32_t litcap_words,
+                uint4 *rec, unsigned int *queue)
+{
+    const uint32_t n_items = min(*item_count, max_items);
+    if (n_items == 0) return;
+    extern __shared__ uint32_t s_tab[];                     // [kDecWarps][kTabEntries][32 lanes] x u16
+    __shared__ uint32_t s_len[32];                          // length symbol - 257 -> len_entry
+    __shared__ uint32_t s_dsym[32];                         // distance symbol -> dist_entry
+    if (threadIdx.x < 29) s_len[threadIdx.x] = len_entry(257 + threadIdx.x);
+    if (threadIdx.x < 32) s_dsym[threadIdx.x] = threadIdx.x < 30 ? dist_entry(threadIdx.x) : 0u;
+    __syncthreads();
+
+    enum { S_IDLE = 0, S_HEADER = 1, S_BLOCK = 2, S_STORED = 3, S_FINISH = 4, S_DONE = 5 };
+    const int lane = threadIdx.x & 31;
+    const LaneTab tab = {reinterpret_cast<uint8_t *>(s_tab) + (size_t)(threadIdx.x >> 5) * kTabEntries * 64 + 2 * lane};
+    SplitScratch *my = scratch + ((size_t)blockIdx.x * (kDecWarps * 32) + threadIdx.x);
+
+    const uint32_t trailer_bytes = (flags & HDLZ_F_RAW) ? 0u : (flags & HDLZ_F_GZIP) ? 8u : 4u;
+    uint32_t state = S_IDLE;
+    uint32_t item = 0, n_in = 0, nfull = 0, tailw = 0;
+    const uint8_t *src = in;
+    const uint32_t *inw = reinterpret_cast<const uint32_t *>(in);
+    uint32_t st = HDLZ_OK;
+    uint32_t o = 0, final_blk = 0, stored_left = 0;
+    // bit reader: the stream bits from bit `p` of w0 on; w1 follows w0, w2 (word `wi`) is fetched one step ahead.
+    // Between symbols p < 32, so a 32-bit peek is one funnel shift and consuming is one add.
+    uint32_t w0 = 0, w1 = 0, w2 = 0, wi = 0, p = 0;
+    uint32_t *tokp = tokbuf, *litp = litbuf;
+    uint32_t ntok = 0, litw = 0, litfill = 0, pend = 0;
+    uint64_t litacc = 0;
+    uint32_t trip = 0;
+
+    auto load_word = [&](uint32_t w) -> uint32_t {
+        uint32_t v = w == nfull ? tailw : 0u;
+        if (w < nfull) v = __ldg(inw + w);
+        return v;
+    };
+    auto advance = [&]() {         // call when p >= 32
+        w0 = w1; w1 = w2;
+        ++wi;
+        w2 = load_word(wi);
+        p -= 32u;
+    };
+    auto peek = [&]() -> uint32_t { return __funnelshift_r(w0, w1, p); };       // p < 32
+    auto bitpos = [&]() -> uint64_t { return (uint64_t)(wi - 2u) * 32u + p; };  // stream bits consumed
+    auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
+    // append nl (1..3) literal bytes (low bytes of lw)
+    auto emit_lits = [&](uint32_t lw, uint32_t nl) {
+        litacc |= (uint64_t)lw << (8u * litfill);
+        litfill += nl;
+        o += nl;
+        pend += nl;
+        if (litfill >= 4u) {
+            litp[litw++] = (uint32_t)litacc;
+            litacc >>= 32;
+            litfill -= 4u;
+        }
+        if (pend >= 252u) {                    // a token holds at most 255 literals: close a literal-only one
+            tokp[ntok++] = pend;
+            pend = 0;
+        }
+    };
+
+    for (;;) {
+        ++trip;
+        // ---- idle lanes take their next stream.  Looked at every 16th trip, and only when a quarter of the
+        // warp is waiting (or nothing else runs): a lane that opens a stream alone parses the block header
+        // and builds its tables with 31 lanes watching.
+        if ((trip & 15u) == 1u) {
+            const uint32_t idle = __ballot_sync(HDLZ_FULL_MASK, state == S_IDLE);
+            const uint32_t busy = __ballot_sync(HDLZ_FULL_MASK, state != S_IDLE && state != S_DONE);
+            if (!idle && !busy) break;
+            if (idle && (__popc(idle) >= 8 || !busy)) {
+                uint32_t base = 0;
+                const int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(queue, (unsigned)__popc(idle));
+                base = __shfl_sync(HDLZ_FULL_MASK, base, leader);
+                if (state == S_IDLE) {
+                    item = base + __popc(idle & ((1u << lane) - 1u));
+                    if (item >= n_items) {
+                        state = S_DONE;
+                    } else {
+                        const uint64_t sid = items[item];
+                        n_in = in_len[sid];
+                        src = in + (in_off ? in_off[sid] : sid * in_stride);
+                        inw = reinterpret_cast<const uint32_t *>(src);
+                        nfull = n_in >> 2;
+                        tokp = tokbuf + (size_t)item * tokcap;
+                        litp = litbuf + (size_t)item * litcap_words;
+                        st = HDLZ_OK;
+                        o = 0; ntok = 0; litw = 0; litfill = 0; pend = 0; litacc = 0;
+                        final_blk = 0; stored_left = 0;
+                        state = S_HEADER;
+                        const Frame frame = parse_frame(src, n_in, flags);
+                        if (frame.status != HDLZ_OK) {
+                            fail(frame.status);
+                        } else {
+                            tailw = 0;
+                            for (uint32_t b = 0; b < (n_in & 3u); ++b) tailw |= (uint32_t)src[4 * nfull + b] << (8 * b);
+                            wi = frame.body >> 2;
+                            p = 8u * (frame.body & 3u);
+                            w0 = load_word(wi);
+                            w1 = load_word(wi + 1);
+                            wi += 2;
+                            w2 = load_word(wi);
+                        }
+                    }
+                }
+            }
+        }
+
+        if (state == S_BLOCK) {
+            // ---- NEXT / INFLATE / D_NEXT: up to three literals and then, if one follows, one length/distance
+            // pair or the end-of-block code, per trip ----
+            if (wi > nfull + 4) fail(HDLZ_ST_TRUNCATED);          // far past the end of the input: a runaway decode
+            else {
+                {
+                    const uint32_t x = peek();
+                    const uint32_t room = out_cap - o;
+                    uint32_t used = 0, nl = 0, lw = 0;
+                    bool go = true;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t e = tab.get(kLitEnt0, (x >> used) & ((1u << kLitBits) - 1u));
+                        go = go && e < (256u << 4) && nl < room;      // a literal within the table, and room for it
+                        if (go) {
+                            lw |= (e >> 4) << (8 * k);
+                            used += e & 15u;
+                            ++nl;
+                        }
+                    }
+                    if (nl) {
+                        p += used;
+                        emit_lits(lw, nl);
+                        if (p >= 32u) advance();
+                    }
+                }
+                const uint32_t x = peek();
+                uint32_t e = tab.get(kLitEnt0, x & ((1u << kLitBits) - 1u));
+                if (e < (256u << 4)) {
+                    // a literal the chain left behind: only when it took three, or when there is no room for it
+                    // (every trip consumes input or leaves the state)
+                    if (o >= out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
+                } else {
+                    // not a literal of the table: a length, the end of the block, or a longer code
+                    if ((e & 15u) == 0) e = split_slow(x, tab, kCntLEnt0, my->sorted_l, kLitBits, my->resume_l);
+                    const uint32_t nb = e & 15u, sym = e >> 4;
+                    if (nb == 0) {
+                        fail(HDLZ_ST_BAD_CODE);                                 // no such code ("Invalid data")
+                    } else if (sym < 256u) {
+                        if (o >= out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
+                        else { p += nb; emit_lits(sym, 1); }
+                    } else if (sym == 256u) {
+                        p += nb;
+                        state = final_blk ? S_FINISH : S_HEADER;
+                        if (final_blk) final_blk = 2;                           // 2 = finished cleanly
+                    } else if (sym > 285u) {
+                        fail(HDLZ_ST_BAD_CODE);                                 // "invalid token" (deflate.py:1559-1560)
+                    } else {
+                        const uint32_t info = s_len[sym - 257u];
+                        const uint32_t eb = info & 15u;
+                        const uint32_t len = (info >> 16) + ((x >> nb) & ((1u << eb) - 1u));    // <= 15 + 5 bits of 32
+                        p += nb + eb;
+                        if (p >= 32u) advance();
+                        const uint32_t y = peek();
+                        uint32_t d = tab.get(kDistEnt0, y & ((1u << kDistBits) - 1u));
+                        if ((d & 15u) == 0) d = split_slow(y, tab, kCntDEnt0, my->sorted_d, kDistBits, my->resume_d);
+                        const uint32_t dnb = d & 15u;
+                        if (dnb == 0 || (d >> 4) >= 30u) {
+                            fail(HDLZ_ST_BAD_CODE);
+                        } else {
+                            const uint32_t de = s_dsym[d >> 4];
+                            const uint32_t deb = de & 15u;
+                            const uint32_t dist = (de >> 8) + ((y >> dnb) & ((1u << deb) - 1u));   // <= 15 + 13 bits of 32
+                            p += dnb + deb;
+                            if (dist > o) fail(HDLZ_ST_DIST_TOO_FAR);            // "distance too big" (deflate.py:1506-1508)
+                            else if (len > out_cap - o) fail(HDLZ_ST_OUT_OVERFLOW);
+                            else {
+                                tokp[ntok++] = pend | (len << 8) | ((dist - 1u) << 17);
+                                pend = 0;
+                                o += len;
+                            }
+                        }
+                    }
+                    if (p >= 32u) advance();
+                }
+            }
+        } else if (state == S_HEADER) {
+            const bool past_end = bitpos() + 3 > 8ull * n_in;
+            const uint32_t hx = peek();
+            final_blk = hx & 1u;
+            const uint32_t type = past_end ? 4u : (hx >> 1) & 3u;
+            p += 3;
+            if (p >= 32u) advance();
+            if (type == 4) {
+                fail(HDLZ_ST_TRUNCATED);                                        // "NO EOF!" (deflate.py:1535-1539)
+            } else if (type == 3) {
+                fail(HDLZ_ST_BAD_BTYPE);                                        // "Bad method" (deflate.py:718-721)
+            } else if (type == 0) {
+                // stored block header (deflate.py:709-717)
+                p = (p + 7u) & ~7u;
+                if (p >= 32u) advance();
+                const uint32_t v = peek();
+                const uint32_t len = v & 0xFFFFu, nlen = v >> 16;
+                p += 32u;
+                advance();
+                const uint64_t bytepos = bitpos() >> 3;
+                if ((len ^ 0xFFFFu) != nlen) fail(HDLZ_ST_BAD_STORED);
+                else if (bytepos + len > n_in) fail(HDLZ_ST_TRUNCATED);
+                else if ((uint64_t)o + len > out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
+                else { stored_left = len; state = S_STORED; }
+            } else {
+                uint8_t *lens = my->lens;
+                uint32_t bad = 0, nlen = 288, ndist = 32;
+                if (type == 1) {
+                    // fixed block (STATIC, deflate.py:1064-1076): the same tables, from the fixed lengths (the two
+                    // unused 5-bit distance codes are built too and rejected on use, like symbols 286 / 287)
+                    for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                    for (int i = 0; i < 32; ++i) lens[288 + i] = 5;
+                } else {
+                    // ---- dynamic block header (BL / READBL / REPEAT, deflate.py:1084-1202) ----
+                    auto get = [&](uint32_t n) -> uint32_t {                    // n <= 16
+                        const uint32_t v = peek() & ((1u << n) - 1u);
+                        p += n;
+                        if (p >= 32u) advance();
+                        return v;
+                    };
+                    nlen = get(5) + 257; ndist = get(5) + 1;
+                    const uint32_t ncode = get(4) + 4;
+                    bad = (nlen > 286 || ndist > 30) ? 1u : 0u;
+                    for (int i = 0; i < 19; ++i) lens[i] = 0;
+                    for (uint32_t i = 0; i < ncode; ++i) lens[c_clorder[i]] = (uint8_t)get(3);
+                    // code-length code: 7-bit table in the distance table's place, its arrays in the distance code's
+                    if (!bad) bad = split_build(lens, 19, tab, kDistEnt0, 7, kCntDEnt0, my->sorted_d, my->resume_d, false);
+                    if (!bad) {
+                        uint32_t any = 0;
+                        for (int l = 1; l <= 7; ++l) any |= tab.get(kCntDEnt0, l);
+                        if (!any) bad = 1;
+                    }
+                    uint32_t idx = 0, prev = 0;
+                    const uint32_t total = nlen + ndist;
+                    while (!bad && idx < total) {
+                        if (wi > nfull + 4) { bad = 2; break; }
+                        const uint32_t e = tab.get(kDistEnt0, peek() & 127u);
+                        const uint32_t nb = e & 15u, sym = e >> 4;
+                        if (nb == 0) { bad = 1; break; }
+                        p += nb;
+                        if (p >= 32u) advance();
+                        uint32_t rep, val;
+                        if (sym < 16) { rep = 1; val = sym; prev = sym; }
+                        else if (sym == 16) {
+                            if (idx == 0) { bad = 1; break; }
+                            rep = 3 + get(2); val = prev;
+                        } else if (sym == 17) { rep = 3 + get(3); val = 0; prev = 0; }
+                        else { rep = 11 + get(7); val = 0; prev = 0; }
+                        if (idx + rep > total) { bad = 1; break; }
+                        for (uint32_t k = 0; k < rep; ++k) lens[idx + k] = (uint8_t)val;
+                        idx += rep;
+                    }
+                    if (!bad && lens[256] == 0) bad = 1;                         // no end-of-block code
+                }
+                if (!bad) bad = split_build(lens + nlen, (int)ndist, tab, kDistEnt0, kDistBits, kCntDEnt0, my->sorted_d, my->resume_d, true);
+                if (!bad) bad = split_build(lens, (int)nlen, tab, kLitEnt0, kLitBits, kCntLEnt0, my->sorted_l, my->resume_l, true);
+                if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
+                else state = S_BLOCK;
+            }
+        } else if (state == S_STORED) {
+            // stored bytes, up to 3 per trip (COPY with method 0, deflate.py:1603-1616); p is a multiple of 8 here
+            uint32_t lw = 0, nl = 0;
+            const uint32_t v = peek();
+            for (int k = 0; k < 3 && stored_left; ++k, --stored_left) {
+                lw |= ((v >> (8 * k)) & 255u) << (8 * k);
+                ++nl;
+            }
+            if (nl) {
+                p += 8u * nl;
+                emit_lits(lw, nl);
+                if (p >= 32u) advance();
+            }
+            if (stored_left == 0) {
+                state = final_blk ? S_FINISH : S_HEADER;
+                if (final_blk) final_blk = 2;
+            }
+        } else if (state == S_FINISH) {
+            // ---- end of a stream: close the token stream, trailer position, record for phase 2 ----
+            uint32_t want = 0;
+            if (st == HDLZ_OK) {
+                if (final_blk != 2) {
+                    st = HDLZ_ST_TRUNCATED;
+                } else {
+                    if (pend) tokp[ntok++] = pend;
+                    if (litfill) litp[litw++] = (uint32_t)litacc;
+                    const uint64_t bp = bitpos();
+                    const uint64_t tp = (bp + 7) >> 3;                           // the trailer (zlib: Adler-32) must be present
+                    if (bp > 8ull * n_in || tp + trailer_bytes > n_in) st = HDLZ_ST_TRUNCATED;   // "NO EOF!" (deflate.py:1535-1539)
+                    else if (trailer_bytes == 4u)
+                        want = ((uint32_t)src[tp] << 24) | ((uint32_t)src[tp + 1] << 16) | ((uint32_t)src[tp + 2] << 8) | src[tp + 3];
+                }
+            }
+            rec[item] = make_uint4(ntok, o, st, want);
+            state = S_IDLE;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// phase 2: token stream -> output, one warp per stream, window in shared memory
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kResWarps * 32, kResCtasPerSm)
+k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, uint32_t max_items,
+                 const uint32_t *__restrict__ tokbuf, uint32_t tokcap, const uint32_t *__restrict__ litbuf,
+                 uint32_t litcap_words, const uint4 *__restrict__ rec, uint8_t *out, uint64_t out_stride,
+                 uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint32_t flags, unsigned int *queue)
+{
+    const uint32_t n_items = min(*item_count, max_items);
+    extern __shared__ uint4 s_win4[];
+    const int lane = threadIdx.x & 31;
+    uint8_t *win = reinterpret_cast<uint8_t *>(s_win4) + (size_t)(threadIdx.x >> 5) * kWinBytes;
+    const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) && !(flags & (HDLZ_F_RAW | HDLZ_F_GZIP));
+
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(queue, 1u);
+        item = __shfl_sync(HDLZ_FULL_MASK, item, 0);
+        if (item >= n_items) break;
+        const uint32_t sid = items[item];
+        const uint4 r = rec[item];
+        if (r.z != HDLZ_OK) {
+            if (lane == 0) {
+                out_len[sid] = 0;
+                if (status) status[sid] = r.z;
+            }
+            continue;
+        }
+        const uint32_t ntok = r.x, o = r.y;
+        const uint32_t *tok = tokbuf + (size_t)item * tokcap;
+        const uint8_t *lit = reinterpret_cast<const uint8_t *>(litbuf + (size_t)item * litcap_words);
+        uint8_t *dst = out + (uint64_t)sid * out_stride;
+
+        uint32_t O0 = 0, L0 = 0;
+        uint32_t tk_next = (uint32_t)lane < ntok ? __ldg(tok + lane) : 0u;
+        for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
+            const uint32_t tk = tk_next;
+            tk_next = t0 + 32 + lane < ntok ? __ldg(tok + t0 + 32 + lane) : 0u;
+            const uint32_t lits = tk & 255u, len = (tk >> 8) & 511u, dist = (tk >> 17) + 1u;
+            // one scan for both cursors: literals consumed in the low half, bytes produced in the high half
+            const uint32_t packed = lits | ((lits + len) << 16);
+            uint32_t incl = packed;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(HDLZ_FULL_MASK, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t total = __shfl_sync(HDLZ_FULL_MASK, incl, 31);
+            const uint32_t excl = incl - packed;
+            const uint8_t *ls = lit + L0 + (excl & 0xFFFFu);
+            uint8_t *wd = win + O0 + (excl >> 16);
+            // ---- literals of the 32 tokens
+            for (uint32_t b = 0; b < lits; b += 4) {
+                uint8_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = b + j < lits ? ls[b + j] : (uint8_t)0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (b + j < lits) wd[b + j] = v[j];
+            }
+            __syncwarp();
+            // ---- copies (COPY, deflate.py:1627-1656): ready when the source ends below the first unresolved copy
+            uint8_t *cd = wd + lits;                 // destination of this lane's copy
+            const uint8_t *cs = cd - dist;
+            uint32_t pending = __ballot_sync(HDLZ_FULL_MASK, len != 0u);
+            while (pending) {
+                const int first = __ffs(pending) - 1;
+                const uint32_t flen = __shfl_sync(HDLZ_FULL_MASK, len, first);
+                const uint32_t fdo = __shfl_sync(HDLZ_FULL_MASK, (uint32_t)(cd - win), first);
+                if (flen > 32u) {
+                    // a long copy, by the whole warp, 32 bytes per step
+                    const uint32_t fdist = __shfl_sync(HDLZ_FULL_MASK, dist, first);
+                    uint8_t *fd = win + fdo;
+                    const uint8_t *fs = fd - fdist;
+                    if (fdist >= 32u) {
+                        for (uint32_t k = 0; k < flen; k += 32) {
+                            if (k + lane < flen) fd[k + lane] = fs[k + lane];
+                            __syncwarp();
+                        }
+                    } else {
+                        // the source is one period of `fdist` final bytes
+                        for (uint32_t k = lane; k < flen; k += 32) fd[k] = fs[k % fdist];
+                        __syncwarp();
+                    }
+                    pending &= ~(1u << first);
+                    continue;
+                }
+                const bool mine = (pending >> lane) & 1u;
+                const bool ready = mine && len <= 32u && (lane == first || (uint32_t)(cs - win) + len <= fdo);
+                const uint32_t rmask = __ballot_sync(HDLZ_FULL_MASK, ready);
+                if (ready) {
+                    if (dist >= len) {
+                        for (uint32_t b = 0; b < len; b += 8) {
+                            uint8_t v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = b + j < len ? cs[b + j] : (uint8_t)0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (b + j < len) cd[b + j] = v[j];
+                        }
+                    } else {
+                        for (uint32_t b = 0; b < len; ++b) cd[b] = cs[b];      // overlapping: byte-serial
+                    }
+                }
+                __syncwarp();
+                pending &= ~rmask;
+            }
+            O0 += total >> 16;
+            L0 += total & 0xFFFFu;
+        }
+        __syncwarp();
+
+        // ---- the finished window -> HBM (coalesced 128-bit stores), Adler-32 from the same reads
+        for (uint32_t k = o + lane; k < ((o + 15u) & ~15u); k += 32) win[k] = 0;
+        __syncwarp();
+        const uint4 *w4 = reinterpret_cast<const uint4 *>(win);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        const uint32_t nvec = (o + 15u) >> 4;
+        unsigned long long s1 = 0, s2 = 0;
+        for (uint32_t v = lane; v < nvec; v += 32) {
+            const uint4 q = w4[v];
+            if (16u * v + 16u <= o) {
+                d4[v] = q;
+            } else {
+                for (uint32_t b = 16u * v; b < o; ++b) dst[b] = win[b];
+            }
+            if (want_adler) {
+                // sum x and sum (o - i) x over the 16 bytes at i = 16 v ..: (o - 16 v) * S - sum j x_j
+                const uint32_t S = __dp4a(q.x, 0x01010101u, __dp4a(q.y, 0x01010101u, __dp4a(q.z, 0x01010101u, __dp4a(q.w, 0x01010101u, 0u))));
+                const uint32_t J = __dp4a(q.x, 0x03020100u, __dp4a(q.y, 0x07060504u, __dp4a(q.z, 0x0B0A0908u, __dp4a(q.w, 0x0F0E0D0Cu, 0u))));
+                s1 += S;
+                s2 += (unsigned long long)(o - 16u * v) * S - J;
+            }
+        }
+        uint32_t stt = HDLZ_OK;
+        if (want_adler) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                s1 += __shfl_xor_sync(HDLZ_FULL_MASK, s1, d);
+                s2 += __shfl_xor_sync(HDLZ_FULL_MASK, s2, d);
+            }
+            const uint32_t a = (uint32_t)((1ull + s1) % 65521ull);
+            const uint32_t b = (uint32_t)(((unsigned long long)o + s2) % 65521ull);
+            if (((b << 16) | a) != r.w) stt = HDLZ_ST_BAD_ADLER;
+        }
+        if (lane == 0) {
+            out_len[sid] = stt == HDLZ_OK ? o : 0;
+            if (status) status[sid] = stt;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+size_t split_slot_bytes(uint32_t out_cap)
+{
+    return (size_t)split_tokcap(out_cap) * 4 + (size_t)split_litcap_words(out_cap) * 4 + sizeof(uint4);
+}
+
+size_t split_scratch_bytes(const hdlz_ctx *ctx)
+{
+    return (size_t)ctx->sm_count * kDecCtasPerSm * (kDecWarps * 32) * sizeof(SplitScratch);
+}
+
+// Runs both phases over the first min(*d_item_count, max_items) entries of d_items.  `pool` holds max_items
+// slots (split_slot_bytes each: records | tokens | literals), `scratch` split_scratch_bytes, `queues` two
+// zeroed counters.
+int launch_inflate_split(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
+                         const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
+                         uint32_t *d_out_len, uint32_t *d_status, uint32_t flags, const uint32_t *d_items,
+                         const uint32_t *d_item_count, uint32_t max_items, void *pool, void *scratch,
+                         unsigned int *queues, cudaStream_t s)
+{
+    if (max_items == 0) return HDLZ_SUCCESS;
+    const uint32_t tokcap = split_tokcap(out_cap), litw = split_litcap_words(out_cap);
+    uint4 *rec = reinterpret_cast<uint4 *>(pool);
+    uint32_t *tokbuf = reinterpret_cast<uint32_t *>(rec + max_items);
+    uint32_t *litbuf = tokbuf + (size_t)max_items * tokcap;
+    const size_t dec_smem = (size_t)kDecWarps * kTabEntries * 64;
+    const size_t res_smem = (size_t)kResWarps * kWinBytes;
+    if (!ctx->split_attr_set) {
+        HDLZ_CUDA(cudaFuncSetAttribute(k_decode_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_decode_tokens, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_resolve_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_resolve_tokens, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->split_attr_set = true;
+    }
+    k_decode_tokens<<<(unsigned)(ctx->sm_count * kDecCtasPerSm), kDecWarps * 32, dec_smem, s>>>(
+        d_in, d_in_off, in_stride, d_in_len, out_cap, flags, d_items, d_item_count, max_items,
+        reinterpret_cast<SplitScratch *>(scratch), tokbuf, tokcap, litbuf, litw, rec, queues);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    k_resolve_tokens<<<(unsigned)(ctx->sm_count * kResCtasPerSm), kResWarps * 32, res_smem, s>>>(
+        d_items, d_item_count, max_items, tokbuf, tokcap, litbuf, litw, rec, d_out, out_stride, d_out_len, d_status,
+        flags, queues + 1);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
+
+}  // namespace hdlz

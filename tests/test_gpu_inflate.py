@@ -89,7 +89,7 @@ def test_multi_block_and_window(engine):
     assert engine.decompress(z, flags=3) == data
 
 
-FORCE_GENERAL, FORCE_LANES, NO_LANE_SCRATCH = 0x100, 0x200, 0x400   # internal routing flags (csrc/hdlz_common.cuh)
+FORCE_GENERAL, FORCE_LANES, NO_LANE_SCRATCH, NO_SPLIT = 0x100, 0x200, 0x400, 0x1000   # internal routing flags (csrc/hdlz_common.cuh)
 
 
 @pytest.mark.parametrize("route", [0, FORCE_GENERAL, FORCE_LANES])
@@ -109,7 +109,7 @@ def test_config3_zfixed_blocks(engine, route):
         assert out.tobytes() == b"".join(blocks)
 
 
-@pytest.mark.parametrize("route", [FORCE_GENERAL, FORCE_LANES, FORCE_LANES | NO_LANE_SCRATCH])
+@pytest.mark.parametrize("route", [FORCE_GENERAL, FORCE_LANES, FORCE_LANES | NO_SPLIT, FORCE_LANES | NO_LANE_SCRATCH])
 def test_routes_agree_on_mixed_and_corrupt_streams(engine, route):
     """Fixed, stored, dynamic (handed over by the lane kernel), long-distance and corrupted streams:
     both routes must give zlib's bytes or an error status, never differ on valid streams."""
@@ -144,7 +144,7 @@ def test_routes_agree_on_mixed_and_corrupt_streams(engine, route):
             assert want is None or len(want) > 6000, (i, status[i])
 
 
-@pytest.mark.parametrize("route,n", [(0, 64), (FORCE_LANES, 64), (0, 1500), (hz.F_PERSIST_TABLES, 1500)])
+@pytest.mark.parametrize("route,n", [(0, 64), (FORCE_LANES, 64), (0, 1500), (NO_SPLIT, 1500), (NO_SPLIT | hz.F_PERSIST_TABLES, 1500)])
 def test_config4_dynamic_32k(engine, route, n):
     """BASELINE config 4 shape: 32 KiB plain, zlib level 6 dynamic trees, OBSIZE = 32768; through the
     warp-per-stream kernel (few streams) and the lane-per-stream kernel with per-lane tables (many)."""
@@ -288,6 +288,76 @@ def test_empty_distance_code_is_rejected_on_every_route(engine, flags):
     for i, s in enumerate(streams):
         buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
     lens = np.array([len(s) for s in streams], dtype=np.uint32)
-    for route in (0, FORCE_GENERAL, FORCE_LANES):
+    for route in (0, FORCE_GENERAL, FORCE_LANES, FORCE_LANES | NO_SPLIT):
         out, out_len, status = engine.decompress_host(buf, lens, 4096, flags=flags | route)
         assert (status[0::2] == 0).all() and (status[1::2] == 3).all(), (route, status[:8])
+
+
+def test_two_phase_route_shapes(engine):
+    """The decode -> resolve route (hdlz_inflate_split.cu) on what stresses its token format: literal runs far
+    beyond 255, copies of every length up to 258 at distances 1 .. 32768 (overlapping and not), stored and
+    fixed blocks mixed into dynamic streams, outputs that are not multiples of 16, raw containers, the pool
+    growing from call to call.  zlib is the expected value."""
+    rnd = random.Random(99)
+    rng = np.random.default_rng(99)
+    plains = []
+    for t in range(1100):
+        kind = t % 11
+        n = rnd.choice([17, 333, 4099, 20000, 32768, 32767, 31001])
+        if kind == 0:
+            d = bytes(rng.integers(0, 256, n, dtype=np.uint8))                      # incompressible: stored blocks / long literal runs
+        elif kind == 1:
+            d = bytes([rnd.randrange(256)]) * n                                      # distance 1, length 258 chains
+        elif kind == 2:
+            p = bytes(rng.integers(97, 123, rnd.choice([2, 3, 5, 31, 33, 257, 259, 4000])))
+            d = (p * (n // len(p) + 1))[:n]                                          # periodic: overlapping copies
+        elif kind == 3:
+            base = bytes(rng.integers(0, 256, 3000, dtype=np.uint8))
+            d = (base + bytes(rng.integers(0, 4, n, dtype=np.uint8)))[:n]
+            d = d + d[:max(0, 32768 - len(d))]                                       # far copies (distance up to 32 KiB)
+            d = d[:32768]
+        elif kind == 4:
+            d = bytes((rng.zipf(1.3, n) % 64 + 32).astype(np.uint8))
+        elif kind == 5:
+            d = " ".join("   Hello World! %d     " % i for i in range(2000)).encode()[:n]
+        elif kind == 6:
+            d = bytes(rng.integers(0, 256, n // 2, dtype=np.uint8)) + bytes(n - n // 2)
+        elif kind == 7:
+            d = workload.block(t, n)
+        elif kind == 8:
+            d = bytes(rng.choice(np.frombuffer(b"ab", dtype=np.uint8), n))
+        elif kind == 9:
+            d = b""
+        else:
+            d = bytes(rng.integers(0, 256, 5, dtype=np.uint8)) * (n // 5)
+        plains.append(d)
+    for wbits, fl in ((15, 0), (-15, hz.F_RAW)):
+        streams = []
+        for i, d in enumerate(plains):
+            lvl, strat = [(6, 0), (9, 0), (1, 0), (6, zlib.Z_FILTERED), (6, zlib.Z_RLE), (6, zlib.Z_HUFFMAN_ONLY)][i % 6]
+            co = zlib.compressobj(lvl, zlib.DEFLATED, wbits, 8, strat)
+            if i % 5 == 0 and len(d) > 100:                                          # several blocks, a stored one in the middle
+                z = co.compress(d[:len(d) // 3]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(d[len(d) // 3:]) + co.flush()
+            else:
+                z = co.compress(d) + co.flush()
+            streams.append(z)
+        stride = (max(len(s) for s in streams) + 15) & ~15
+        buf = np.zeros((len(streams), stride), dtype=np.uint8)
+        for i, s in enumerate(streams):
+            buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+        lens = np.array([len(s) for s in streams], dtype=np.uint32)
+        for rep in range(2):                                                         # second call: the pool has grown to the demand
+            out, out_len, status = engine.decompress_host(buf, lens, 32768, flags=fl | (hz.F_VERIFY_ADLER if rep else 0))
+            assert not status.any(), (wbits, rep, np.nonzero(status)[0][:8], status[status != 0][:8])
+            for i, d in enumerate(plains):
+                assert out_len[i] == len(d) and out[i, :len(d)].tobytes() == d, (wbits, rep, i)
+    # a wrong Adler-32 is caught by phase 2, a too small out_cap by phase 1
+    z = bytearray(zl(plains[4], 6))
+    z[-1] ^= 0x55
+    bad = np.zeros((1100, (len(z) + 15) & ~15), dtype=np.uint8)
+    bad[:, :len(z)] = np.frombuffer(bytes(z), dtype=np.uint8)
+    blens = np.full(1100, len(z), dtype=np.uint32)
+    _, _, status = engine.decompress_host(bad, blens, 32768, flags=hz.F_VERIFY_ADLER)
+    assert (status == 9).all()
+    _, _, status = engine.decompress_host(bad, blens, len(plains[4]) - 1, flags=0)
+    assert (status == 6).all()
