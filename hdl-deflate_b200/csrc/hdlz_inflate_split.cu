@@ -12,13 +12,13 @@
 //            decode that resumes after the table's bits.  Output: a compact token stream in global
 //            memory — literal bytes, and one 32-bit token per copy
 //                bits 0..7 literals before the copy | 8..16 copy length (0 = none) | 17..31 distance - 1.
-//   phase 2  k_resolve_tokens  one WARP per stream, the stream's whole output (<= 32 KiB) staged in
-//            shared memory.  32 tokens per step: one packed warp scan gives every token its literal
-//            source and its output position, the lanes place their literals and then their copies —
-//            a copy runs as soon as its source lies below the first unresolved copy of the step
-//            (almost always at once: level-6 distances are far); copies longer than 32 bytes are done
-//            by the whole warp.  The finished window goes to HBM with coalesced 128-bit stores, and
-//            the optional Adler-32 is taken from the same 128-bit reads.
+//   phase 2  k_resolve_tokens  one CTA of eight warps per stream, the stream's whole output (<= 32 KiB)
+//            staged in shared memory (six streams per SM).  256 tokens per step, one per thread: a block
+//            scan gives every token its literal source and its output position; the threads place their
+//            literals, then their copies in rounds — a bit per output byte says whether it is final, and a
+//            copy runs in the first round in which all it reads is (level-6 copies reach far back: mostly
+//            the first); copies longer than 32 bytes are done by a whole warp.  The finished window goes
+//            to HBM with coalesced 128-bit stores, and the optional Adler-32 is taken from the same reads.
 //
 // Algorithmic HBM traffic per stream: C bytes read + L bytes written; the token stream adds its
 // own write + read (about 0.8 L on level-6 data).
@@ -44,9 +44,10 @@ constexpr int kCntLEnt0 = kDistEnt0 + (1 << kDistBits);       // 16 codes per le
 constexpr int kCntDEnt0 = kCntLEnt0 + 16;                     // 16, distance code (and the code-length code)
 constexpr int kTabEntries = kCntDEnt0 + 16;                   // 416 entries = 832 B per lane
 
-constexpr int kResWarps = 2;
-constexpr int kResCtasPerSm = 3;
+constexpr int kResThreads = 256;
+constexpr int kResCtasPerSm = 6;
 constexpr int kWinBytes = (int)kSplitMaxOut + 16;             // the output of one stream + a zeroed tail to 16 bytes
+constexpr int kBitmapBytes = ((int)kSplitMaxOut + 32) / 8 + 12;   // one bit per window byte, a spare word, padded to 16
 
 __constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 __constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35,
@@ -154,7 +155,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 {
     const uint32_t n_items = min(*item_count, max_items);
     if (n_items == 0) return;
-    extern __shared__ uint32_t s_tab[];                     // [kDecWarps][kTabEntries][32 lanes] x u16
+    extern __shared__ uint32_t s_tab[];                     // [kDecWarps][kTabEntries][32 lanes] x u16, then the input rings
     __shared__ uint32_t s_len[32];                          // length symbol - 257 -> len_entry
     __shared__ uint32_t s_dsym[32];                         // distance symbol -> dist_entry
     if (threadIdx.x < 29) s_len[threadIdx.x] = len_entry(257 + threadIdx.x);
@@ -165,6 +166,8 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     const int lane = threadIdx.x & 31;
     const LaneTab tab = {reinterpret_cast<uint8_t *>(s_tab) + (size_t)(threadIdx.x >> 5) * kTabEntries * 64 + 2 * lane};
     SplitScratch *my = scratch + ((size_t)blockIdx.x * (kDecWarps * 32) + threadIdx.x);
+    // input ring of this lane: two slots of four words; slot s at ring[s * 128 .. +4) (16 bytes per lane, 512 per slot)
+    uint32_t *ring = s_tab + (size_t)kDecWarps * kTabEntries * 16 + (size_t)(threadIdx.x >> 5) * 256 + 4 * lane;
 
     const uint32_t trailer_bytes = (flags & HDLZ_F_RAW) ? 0u : (flags & HDLZ_F_GZIP) ? 8u : 4u;
     uint32_t state = S_IDLE;
@@ -173,27 +176,56 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     const uint32_t *inw = reinterpret_cast<const uint32_t *>(in);
     uint32_t st = HDLZ_OK;
     uint32_t o = 0, final_blk = 0, stored_left = 0;
-    // bit reader: the stream bits from bit `p` of w0 on; w1 follows w0, w2 (word `wi`) is fetched one step ahead.
-    // Between symbols p < 32, so a 32-bit peek is one funnel shift and consuming is one add.
-    uint32_t w0 = 0, w1 = 0, w2 = 0, wi = 0, p = 0;
+    // bit reader: the stream bits from bit `p` of w0 on; w1, w2 follow.  Between symbols p < 32, so a 32-bit
+    // peek is one funnel shift and consuming is one add.  The words come out of a two-vector ring in shared
+    // memory that cp.async fills a whole 16-byte vector ahead — straight from global to shared memory, so no
+    // register waits for the load (a register prefetch was copied at every loop merge and stalled there).
+    uint32_t w0 = 0, w1 = 0, w2 = 0, wi = 0, p = 0;         // wi = stream word index of w0
+    uint32_t rp = 0, vi = 0, m4 = 0;                         // ring read position 0..7, next vector to fetch, (src & 15) / 4
     uint32_t *tokp = tokbuf, *litp = litbuf;
     uint32_t ntok = 0, litw = 0, litfill = 0, pend = 0;
     uint64_t litacc = 0;
     uint32_t trip = 0;
 
-    auto load_word = [&](uint32_t w) -> uint32_t {
-        uint32_t v = w == nfull ? tailw : 0u;
-        if (w < nfull) v = __ldg(inw + w);
+    auto load_word = [&](int64_t w) -> uint32_t {           // stream word w; zero outside the stream
+        uint32_t v = w == (int64_t)nfull ? tailw : 0u;
+        if (w >= 0 && w < (int64_t)nfull) v = __ldg(inw + w);
         return v;
+    };
+    auto fetch_vec = [&](uint32_t v, uint32_t slot) {        // 16-byte aligned vector v (stream words 4 v - m4 ..) -> ring slot
+        const int64_t i0 = (int64_t)4 * v - m4;
+        uint32_t *dstw = ring + slot * 128;                  // this lane's four words of the slot
+        if (i0 >= 0 && i0 + 4 <= (int64_t)nfull) {
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dstw);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(inw + i0) : "memory");
+        } else {
+            dstw[0] = load_word(i0); dstw[1] = load_word(i0 + 1); dstw[2] = load_word(i0 + 2); dstw[3] = load_word(i0 + 3);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto pop = [&]() -> uint32_t {
+        const uint32_t r = ring[(rp >> 2) * 128 + (rp & 3u)];
+        rp = (rp + 1u) & 7u;
+        if ((rp & 3u) == 0) {
+            // the slot just read is free: the vector after next goes there; the next one (asked for four words
+            // ago) must have landed before it is read
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            fetch_vec(vi, (rp >> 2) ^ 1u);
+            ++vi;
+        }
+        return r;
     };
     auto advance = [&]() {         // call when p >= 32
         w0 = w1; w1 = w2;
+        w2 = pop();
         ++wi;
-        w2 = load_word(wi);
         p -= 32u;
     };
     auto peek = [&]() -> uint32_t { return __funnelshift_r(w0, w1, p); };       // p < 32
-    auto bitpos = [&]() -> uint64_t { return (uint64_t)(wi - 2u) * 32u + p; };  // stream bits consumed
+    auto peek_at = [&](uint32_t pp) -> uint32_t {                              // pp < 64
+        return __funnelshift_r(pp < 32u ? w0 : w1, pp < 32u ? w1 : w2, pp & 31u);
+    };
+    auto bitpos = [&]() -> uint64_t { return (uint64_t)wi * 32u + p; };         // stream bits consumed
     auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
     // append nl (1..3) literal bytes (low bytes of lw)
     auto emit_lits = [&](uint32_t lw, uint32_t nl) {
@@ -214,14 +246,14 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
     for (;;) {
         ++trip;
-        // ---- idle lanes take their next stream.  Looked at every 16th trip, and only when a quarter of the
-        // warp is waiting (or nothing else runs): a lane that opens a stream alone parses the block header
+        // ---- idle lanes take their next stream.  Looked at every 16th trip, and only when four lanes
+        // are waiting (or nothing else runs): a lane that opens a stream alone parses the block header
         // and builds its tables with 31 lanes watching.
         if ((trip & 15u) == 1u) {
             const uint32_t idle = __ballot_sync(HDLZ_FULL_MASK, state == S_IDLE);
             const uint32_t busy = __ballot_sync(HDLZ_FULL_MASK, state != S_IDLE && state != S_DONE);
             if (!idle && !busy) break;
-            if (idle && (__popc(idle) >= 8 || !busy)) {
+            if (idle && (__popc(idle) >= 4 || !busy)) {
                 uint32_t base = 0;
                 const int leader = __ffs(idle) - 1;
                 if (lane == leader) base = atomicAdd(queue, (unsigned)__popc(idle));
@@ -248,12 +280,17 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         } else {
                             tailw = 0;
                             for (uint32_t b = 0; b < (n_in & 3u); ++b) tailw |= (uint32_t)src[4 * nfull + b] << (8 * b);
+                            m4 = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u) >> 2;
                             wi = frame.body >> 2;
                             p = 8u * (frame.body & 3u);
-                            w0 = load_word(wi);
-                            w1 = load_word(wi + 1);
-                            wi += 2;
-                            w2 = load_word(wi);
+                            const uint32_t a = wi + m4;                          // aligned word index of the first word
+                            vi = a >> 2;
+                            fetch_vec(vi, 0);
+                            fetch_vec(vi + 1, 1);
+                            vi += 2;
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            rp = a & 3u;
+                            w0 = pop(); w1 = pop(); w2 = pop();
                         }
                     }
                 }
@@ -262,7 +299,9 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
         if (state == S_BLOCK) {
             // ---- NEXT / INFLATE / D_NEXT: up to three literals and then, if one follows, one length/distance
-            // pair or the end-of-block code, per trip ----
+            // pair, per trip.  The common path is branch-free (the lanes of a warp sit in different places of
+            // their streams: a branch costs the whole warp both sides); whatever else the next symbol is — end
+            // of block, a code longer than the tables, anything invalid — goes through `other` below.
             if (wi > nfull + 4) fail(HDLZ_ST_TRUNCATED);          // far past the end of the input: a runaway decode
             else {
                 {
@@ -274,62 +313,88 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     for (int k = 0; k < 3; ++k) {
                         const uint32_t e = tab.get(kLitEnt0, (x >> used) & ((1u << kLitBits) - 1u));
                         go = go && e < (256u << 4) && nl < room;      // a literal within the table, and room for it
-                        if (go) {
-                            lw |= (e >> 4) << (8 * k);
-                            used += e & 15u;
-                            ++nl;
-                        }
+                        lw |= go ? (e >> 4) << (8 * k) : 0u;
+                        used += go ? e & 15u : 0u;
+                        nl += go ? 1u : 0u;
                     }
-                    if (nl) {
-                        p += used;
-                        emit_lits(lw, nl);
-                        if (p >= 32u) advance();
+                    p += used;
+                    // the literals (possibly none) join the literal stream
+                    litacc |= (uint64_t)lw << (8u * litfill);
+                    litfill += nl;
+                    o += nl;
+                    pend += nl;
+                    if (litfill >= 4u) {
+                        litp[litw++] = (uint32_t)litacc;
+                        litacc >>= 32;
+                        litfill -= 4u;
                     }
+                    if (pend >= 252u) {                    // a token holds at most 255 literals: close a literal-only one
+                        tokp[ntok++] = pend;
+                        pend = 0;
+                    }
+                    if (p >= 32u) advance();
                 }
                 const uint32_t x = peek();
-                uint32_t e = tab.get(kLitEnt0, x & ((1u << kLitBits) - 1u));
-                if (e < (256u << 4)) {
-                    // a literal the chain left behind: only when it took three, or when there is no room for it
-                    // (every trip consumes input or leaves the state)
-                    if (o >= out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
-                } else {
-                    // not a literal of the table: a length, the end of the block, or a longer code
-                    if ((e & 15u) == 0) e = split_slow(x, tab, kCntLEnt0, my->sorted_l, kLitBits, my->resume_l);
-                    const uint32_t nb = e & 15u, sym = e >> 4;
-                    if (nb == 0) {
+                const uint32_t e = tab.get(kLitEnt0, x & ((1u << kLitBits) - 1u));
+                const uint32_t nb = e & 15u, ls = (e >> 4) - 257u;
+                const bool is_len = ls < 29u && nb != 0u;                     // a length symbol of the table
+                const uint32_t info = s_len[is_len ? ls : 0u];
+                const uint32_t eb = info & 15u;
+                const uint32_t len = (info >> 16) + ((x >> nb) & ((1u << eb) - 1u));    // <= 8 + 5 bits of 32
+                const uint32_t p2 = p + nb + eb;                                // < 32 + 13
+                const uint32_t y = peek_at(p2);
+                const uint32_t d = tab.get(kDistEnt0, y & ((1u << kDistBits) - 1u));
+                const uint32_t dnb = d & 15u, dsym = (d >> 4) & 31u;
+                const uint32_t de = s_dsym[dsym];
+                const uint32_t deb = de & 15u;
+                const uint32_t dist = (de >> 8) + ((y >> dnb) & ((1u << deb) - 1u));   // <= 7 + 13 bits of 32
+                const bool copy = is_len && dnb != 0u && (d >> 4) < 30u && dist <= o && len <= out_cap - o;
+                if (copy) {
+                    p = p2 + dnb + deb;                                         // < 45 + 20
+                    tokp[ntok++] = pend | (len << 8) | ((dist - 1u) << 17);
+                    pend = 0;
+                    o += len;
+                    if (p >= 32u) advance();
+                    if (p >= 32u) advance();
+                } else if (e >= (256u << 4) || o >= out_cap) {
+                    // ---- `other`: not a copy the tables decode, and not a literal the next trip takes
+                    uint32_t e2 = e;
+                    if ((e2 & 15u) == 0) e2 = split_slow(x, tab, kCntLEnt0, my->sorted_l, kLitBits, my->resume_l);
+                    const uint32_t nb2 = e2 & 15u, sym = e2 >> 4;
+                    if (nb2 == 0) {
                         fail(HDLZ_ST_BAD_CODE);                                 // no such code ("Invalid data")
                     } else if (sym < 256u) {
                         if (o >= out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
-                        else { p += nb; emit_lits(sym, 1); }
+                        else { p += nb2; emit_lits(sym, 1); }
                     } else if (sym == 256u) {
-                        p += nb;
+                        p += nb2;
                         state = final_blk ? S_FINISH : S_HEADER;
                         if (final_blk) final_blk = 2;                           // 2 = finished cleanly
                     } else if (sym > 285u) {
                         fail(HDLZ_ST_BAD_CODE);                                 // "invalid token" (deflate.py:1559-1560)
                     } else {
-                        const uint32_t info = s_len[sym - 257u];
-                        const uint32_t eb = info & 15u;
-                        const uint32_t len = (info >> 16) + ((x >> nb) & ((1u << eb) - 1u));    // <= 15 + 5 bits of 32
-                        p += nb + eb;
+                        const uint32_t info2 = s_len[sym - 257u];
+                        const uint32_t eb2 = info2 & 15u;
+                        const uint32_t len2 = (info2 >> 16) + ((x >> nb2) & ((1u << eb2) - 1u));    // <= 15 + 5 bits of 32
+                        p += nb2 + eb2;
                         if (p >= 32u) advance();
-                        const uint32_t y = peek();
-                        uint32_t d = tab.get(kDistEnt0, y & ((1u << kDistBits) - 1u));
-                        if ((d & 15u) == 0) d = split_slow(y, tab, kCntDEnt0, my->sorted_d, kDistBits, my->resume_d);
-                        const uint32_t dnb = d & 15u;
-                        if (dnb == 0 || (d >> 4) >= 30u) {
+                        const uint32_t y2 = peek();
+                        uint32_t d2 = tab.get(kDistEnt0, y2 & ((1u << kDistBits) - 1u));
+                        if ((d2 & 15u) == 0) d2 = split_slow(y2, tab, kCntDEnt0, my->sorted_d, kDistBits, my->resume_d);
+                        const uint32_t dnb2 = d2 & 15u;
+                        if (dnb2 == 0 || (d2 >> 4) >= 30u) {
                             fail(HDLZ_ST_BAD_CODE);
                         } else {
-                            const uint32_t de = s_dsym[d >> 4];
-                            const uint32_t deb = de & 15u;
-                            const uint32_t dist = (de >> 8) + ((y >> dnb) & ((1u << deb) - 1u));   // <= 15 + 13 bits of 32
-                            p += dnb + deb;
-                            if (dist > o) fail(HDLZ_ST_DIST_TOO_FAR);            // "distance too big" (deflate.py:1506-1508)
-                            else if (len > out_cap - o) fail(HDLZ_ST_OUT_OVERFLOW);
+                            const uint32_t de2 = s_dsym[d2 >> 4];
+                            const uint32_t deb2 = de2 & 15u;
+                            const uint32_t dist2 = (de2 >> 8) + ((y2 >> dnb2) & ((1u << deb2) - 1u));   // <= 15 + 13 bits
+                            p += dnb2 + deb2;
+                            if (dist2 > o) fail(HDLZ_ST_DIST_TOO_FAR);           // "distance too big" (deflate.py:1506-1508)
+                            else if (len2 > out_cap - o) fail(HDLZ_ST_OUT_OVERFLOW);
                             else {
-                                tokp[ntok++] = pend | (len << 8) | ((dist - 1u) << 17);
+                                tokp[ntok++] = pend | (len2 << 8) | ((dist2 - 1u) << 17);
                                 pend = 0;
-                                o += len;
+                                o += len2;
                             }
                         }
                     }
@@ -455,9 +520,44 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// phase 2: token stream -> output, one warp per stream, window in shared memory
+// phase 2: token stream -> output, one CTA (8 warps) per stream, window in shared memory
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kResWarps * 32, kResCtasPerSm)
+// bits [start, start + n) of the byte-is-pending bitmap, n <= 32
+__device__ __forceinline__ void range_masks(uint32_t start, uint32_t n, uint32_t &w, uint32_t &m0, uint32_t &m1)
+{
+    w = start >> 5;
+    const uint32_t sh = start & 31u;
+    const unsigned long long m = ((n >= 32u ? 0xFFFFFFFFull : ((1ull << n) - 1ull))) << sh;
+    m0 = (uint32_t)m;
+    m1 = (uint32_t)(m >> 32);
+}
+
+__device__ __forceinline__ bool range_clear(const uint32_t *bm, uint32_t start, uint32_t n)      // n <= 32
+{
+    uint32_t w, m0, m1;
+    range_masks(start, n, w, m0, m1);
+    bool ok = (bm[w] & m0) == 0u;
+    if (m1) ok = ok && (bm[w + 1] & m1) == 0u;
+    return ok;
+}
+
+__device__ __forceinline__ void range_unmark(uint32_t *bm, uint32_t start, uint32_t n)           // n <= 32
+{
+    uint32_t w, m0, m1;
+    range_masks(start, n, w, m0, m1);
+    atomicAnd(bm + w, ~m0);
+    if (m1) atomicAnd(bm + w + 1, ~m1);
+}
+
+__device__ __forceinline__ void range_mark(uint32_t *bm, uint32_t start, uint32_t n)             // n <= 32
+{
+    uint32_t w, m0, m1;
+    range_masks(start, n, w, m0, m1);
+    atomicOr(bm + w, m0);
+    if (m1) atomicOr(bm + w + 1, m1);
+}
+
+__global__ void __launch_bounds__(kResThreads, kResCtasPerSm)
 k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict__ item_count, uint32_t max_items,
                  const uint32_t *__restrict__ tokbuf, uint32_t tokcap, const uint32_t *__restrict__ litbuf,
                  uint32_t litcap_words, const uint4 *__restrict__ rec, uint8_t *out, uint64_t out_stride,
@@ -465,19 +565,24 @@ k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict_
 {
     const uint32_t n_items = min(*item_count, max_items);
     extern __shared__ uint4 s_win4[];
-    const int lane = threadIdx.x & 31;
-    uint8_t *win = reinterpret_cast<uint8_t *>(s_win4) + (size_t)(threadIdx.x >> 5) * kWinBytes;
+    uint8_t *win = reinterpret_cast<uint8_t *>(s_win4);                       // the stream's output
+    uint32_t *bm = reinterpret_cast<uint32_t *>(win + kWinBytes);             // bit i: byte i of the window waits for a copy of the current step
+    __shared__ unsigned long long s_wsum[kResThreads / 32];
+    __shared__ unsigned long long s_red[2][kResThreads / 32];
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_adler = (flags & HDLZ_F_VERIFY_ADLER) && !(flags & (HDLZ_F_RAW | HDLZ_F_GZIP));
 
     for (;;) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(queue, 1u);
-        item = __shfl_sync(HDLZ_FULL_MASK, item, 0);
+        __syncthreads();                                   // the previous stream's window is no longer read
+        if (tid == 0) s_item = atomicAdd(queue, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
         if (item >= n_items) break;
         const uint32_t sid = items[item];
         const uint4 r = rec[item];
         if (r.z != HDLZ_OK) {
-            if (lane == 0) {
+            if (tid == 0) {
                 out_len[sid] = 0;
                 if (status) status[sid] = r.z;
             }
@@ -487,94 +592,145 @@ k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict_
         const uint32_t *tok = tokbuf + (size_t)item * tokcap;
         const uint8_t *lit = reinterpret_cast<const uint8_t *>(litbuf + (size_t)item * litcap_words);
         uint8_t *dst = out + (uint64_t)sid * out_stride;
+        for (uint32_t i = tid; i < (kSplitMaxOut + 32) / 32; i += kResThreads) bm[i] = 0;
+        __syncthreads();
 
         uint32_t O0 = 0, L0 = 0;
-        uint32_t tk_next = (uint32_t)lane < ntok ? __ldg(tok + lane) : 0u;
-        for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
-            const uint32_t tk = tk_next;
-            tk_next = t0 + 32 + lane < ntok ? __ldg(tok + t0 + 32 + lane) : 0u;
+        for (uint32_t t0 = 0; t0 < ntok; t0 += kResThreads) {
+            const uint32_t tk = t0 + tid < ntok ? __ldg(tok + t0 + tid) : 0u;
             const uint32_t lits = tk & 255u, len = (tk >> 8) & 511u, dist = (tk >> 17) + 1u;
-            // one scan for both cursors: literals consumed in the low half, bytes produced in the high half
-            const uint32_t packed = lits | ((lits + len) << 16);
-            uint32_t incl = packed;
+            // block scan of both cursors: literals consumed in the low half, bytes produced in the high half
+            const unsigned long long packed = (unsigned long long)lits | ((unsigned long long)(lits + len) << 32);
+            unsigned long long incl = packed;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(HDLZ_FULL_MASK, incl, d);
+                const unsigned long long v = __shfl_up_sync(HDLZ_FULL_MASK, incl, d);
                 if (lane >= d) incl += v;
             }
-            const uint32_t total = __shfl_sync(HDLZ_FULL_MASK, incl, 31);
-            const uint32_t excl = incl - packed;
-            const uint8_t *ls = lit + L0 + (excl & 0xFFFFu);
-            uint8_t *wd = win + O0 + (excl >> 16);
-            // ---- literals of the 32 tokens
-            for (uint32_t b = 0; b < lits; b += 4) {
-                uint8_t v[4];
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            unsigned long long before = 0, total = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = b + j < lits ? ls[b + j] : (uint8_t)0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (b + j < lits) wd[b + j] = v[j];
+            for (int w = 0; w < kResThreads / 32; ++w) {
+                const unsigned long long v = s_wsum[w];
+                if (w < warp) before += v;
+                total += v;
             }
-            __syncwarp();
-            // ---- copies (COPY, deflate.py:1627-1656): ready when the source ends below the first unresolved copy
-            uint8_t *cd = wd + lits;                 // destination of this lane's copy
-            const uint8_t *cs = cd - dist;
-            uint32_t pending = __ballot_sync(HDLZ_FULL_MASK, len != 0u);
-            while (pending) {
-                const int first = __ffs(pending) - 1;
-                const uint32_t flen = __shfl_sync(HDLZ_FULL_MASK, len, first);
-                const uint32_t fdo = __shfl_sync(HDLZ_FULL_MASK, (uint32_t)(cd - win), first);
-                if (flen > 32u) {
-                    // a long copy, by the whole warp, 32 bytes per step
-                    const uint32_t fdist = __shfl_sync(HDLZ_FULL_MASK, dist, first);
-                    uint8_t *fd = win + fdo;
-                    const uint8_t *fs = fd - fdist;
+            const unsigned long long excl = before + incl - packed;
+            const uint32_t lx = (uint32_t)excl;              // literals before this token (within the step)
+            const uint32_t ooff = O0 + (uint32_t)(excl >> 32);
+            const uint32_t cd = ooff + lits;                 // destination of this thread's copy
+            const uint32_t cs = cd - dist;
+            const uint32_t need = len < dist ? len : dist;   // an overlapping copy only reads `dist` bytes it did not write
+            // every byte a copy of this step will write is marked pending; what the bitmap does not mark is final
+            // (literals included, once the barrier below has passed)
+            for (uint32_t b = 0; b < len; b += 32) range_mark(bm, cd + b, min(32u, len - b));
+            // ---- literals of the warp's 32 tokens, one byte per lane per pass: they are contiguous in the
+            // literal stream, the destination comes from the token that owns the byte (binary search over the
+            // warp's prefix)
+            {
+                const uint32_t l0 = __shfl_sync(HDLZ_FULL_MASK, lx, 0);
+                const uint32_t l1 = __shfl_sync(HDLZ_FULL_MASK, lx + lits, 31);
+                const uint8_t *lsw = lit + L0 + l0;
+                for (uint32_t g0 = 0; g0 < l1 - l0; g0 += 32) {          // warp-uniform trip count: the shuffles need all lanes
+                    const uint32_t g = g0 + lane;
+                    const bool act = g < l1 - l0;
+                    const uint32_t v = act ? lsw[g] : 0u;
+                    // last token t with lx[t] - l0 <= g
+                    uint32_t t = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const uint32_t probe = __shfl_sync(HDLZ_FULL_MASK, lx, (t + step) & 31);
+                        if (probe - l0 <= g) t += step;
+                    }
+                    const uint32_t tl = __shfl_sync(HDLZ_FULL_MASK, lx, t);
+                    const uint32_t to = __shfl_sync(HDLZ_FULL_MASK, ooff, t);
+                    if (act) win[to + (g - (tl - l0))] = (uint8_t)v;
+                }
+            }
+            __syncthreads();
+            // ---- copies (COPY, deflate.py:1627-1656): a copy runs in the first round in which nothing it reads
+            // is pending.  Rounds are separated by a CTA barrier; their number is the depth of the longest
+            // chain of copies reading each other inside these 256 tokens (a handful).
+            bool pending = len != 0u;
+            for (;;) {
+                bool ready = false;
+                if (pending) {
+                    ready = true;
+                    for (uint32_t b = 0; b < need && ready; b += 32) ready = range_clear(bm, cs + b, min(32u, need - b));
+                }
+                // short copies that do not overlap their source: all their bytes as one list, a byte per lane per pass
+                {
+                    const bool flat = ready && len <= 32u && dist >= len;
+                    const uint32_t fl = flat ? len : 0u;
+                    uint32_t fi = fl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(HDLZ_FULL_MASK, fi, d);
+                        if (lane >= d) fi += v;
+                    }
+                    const uint32_t fx = fi - fl;             // bytes of the list before this token
+                    const uint32_t ftot = __shfl_sync(HDLZ_FULL_MASK, fi, 31);
+                    for (uint32_t g0 = 0; g0 < ftot; g0 += 32) {            // warp-uniform trip count
+                        const uint32_t g = g0 + lane;
+                        uint32_t t = 0;
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1) {
+                            const uint32_t probe = __shfl_sync(HDLZ_FULL_MASK, fx, (t + step) & 31);
+                            if (probe <= g) t += step;
+                        }
+                        // tokens without bytes share their successor's prefix: the search lands on the last of
+                        // them, the owner is the first token at or after it that has bytes... the prefix is
+                        // non-decreasing, so take the LAST token whose prefix is <= g: it owns g iff it has bytes,
+                        // and it does, because a token without bytes has the same prefix as its successor
+                        const uint32_t tx = __shfl_sync(HDLZ_FULL_MASK, fx, t);
+                        const uint32_t td = __shfl_sync(HDLZ_FULL_MASK, cd, t);
+                        const uint32_t ts = __shfl_sync(HDLZ_FULL_MASK, cs, t);
+                        if (g < ftot) win[td + (g - tx)] = win[ts + (g - tx)];
+                    }
+                }
+                // short copies that overlap their source: byte-serial by their thread
+                if (ready && len <= 32u && dist < len)
+                    for (uint32_t b = 0; b < len; ++b) win[cd + b] = win[cs + b];
+                // long copies: the whole warp, 32 bytes per step
+                uint32_t longs = __ballot_sync(HDLZ_FULL_MASK, ready && len > 32u);
+                while (longs) {
+                    const int src_lane = __ffs(longs) - 1;
+                    longs &= longs - 1;
+                    const uint32_t fd = __shfl_sync(HDLZ_FULL_MASK, cd, src_lane);
+                    const uint32_t fdist = __shfl_sync(HDLZ_FULL_MASK, dist, src_lane);
+                    const uint32_t flen = __shfl_sync(HDLZ_FULL_MASK, len, src_lane);
                     if (fdist >= 32u) {
                         for (uint32_t k = 0; k < flen; k += 32) {
-                            if (k + lane < flen) fd[k + lane] = fs[k + lane];
+                            if (k + lane < flen) win[fd + k + lane] = win[fd - fdist + k + lane];
                             __syncwarp();
                         }
                     } else {
                         // the source is one period of `fdist` final bytes
-                        for (uint32_t k = lane; k < flen; k += 32) fd[k] = fs[k % fdist];
+                        for (uint32_t k = lane; k < flen; k += 32) win[fd + k] = win[fd - fdist + k % fdist];
                         __syncwarp();
-                    }
-                    pending &= ~(1u << first);
-                    continue;
-                }
-                const bool mine = (pending >> lane) & 1u;
-                const bool ready = mine && len <= 32u && (lane == first || (uint32_t)(cs - win) + len <= fdo);
-                const uint32_t rmask = __ballot_sync(HDLZ_FULL_MASK, ready);
-                if (ready) {
-                    if (dist >= len) {
-                        for (uint32_t b = 0; b < len; b += 8) {
-                            uint8_t v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = b + j < len ? cs[b + j] : (uint8_t)0;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (b + j < len) cd[b + j] = v[j];
-                        }
-                    } else {
-                        for (uint32_t b = 0; b < len; ++b) cd[b] = cs[b];      // overlapping: byte-serial
                     }
                 }
                 __syncwarp();
-                pending &= ~rmask;
+                if (ready) {
+                    __threadfence_block();                   // a thread still checking this round may already see the bits
+                    for (uint32_t b = 0; b < len; b += 32) range_unmark(bm, cd + b, min(32u, len - b));
+                    pending = false;
+                }
+                if (!__syncthreads_or(pending)) break;
             }
-            O0 += total >> 16;
-            L0 += total & 0xFFFFu;
+            O0 += (uint32_t)(total >> 32);
+            L0 += (uint32_t)total;
         }
-        __syncwarp();
 
         // ---- the finished window -> HBM (coalesced 128-bit stores), Adler-32 from the same reads
-        for (uint32_t k = o + lane; k < ((o + 15u) & ~15u); k += 32) win[k] = 0;
-        __syncwarp();
+        for (uint32_t k = o + tid; k < ((o + 15u) & ~15u); k += kResThreads) win[k] = 0;
+        __syncthreads();
         const uint4 *w4 = reinterpret_cast<const uint4 *>(win);
         uint4 *d4 = reinterpret_cast<uint4 *>(dst);
         const uint32_t nvec = (o + 15u) >> 4;
         unsigned long long s1 = 0, s2 = 0;
-        for (uint32_t v = lane; v < nvec; v += 32) {
+        for (uint32_t v = tid; v < nvec; v += kResThreads) {
             const uint4 q = w4[v];
             if (16u * v + 16u <= o) {
                 d4[v] = q;
@@ -596,15 +752,20 @@ k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict_
                 s1 += __shfl_xor_sync(HDLZ_FULL_MASK, s1, d);
                 s2 += __shfl_xor_sync(HDLZ_FULL_MASK, s2, d);
             }
-            const uint32_t a = (uint32_t)((1ull + s1) % 65521ull);
-            const uint32_t b = (uint32_t)(((unsigned long long)o + s2) % 65521ull);
-            if (((b << 16) | a) != r.w) stt = HDLZ_ST_BAD_ADLER;
+            if (lane == 0) { s_red[0][warp] = s1; s_red[1][warp] = s2; }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long t1 = 0, t2 = 0;
+                for (int w = 0; w < kResThreads / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+                const uint32_t a = (uint32_t)((1ull + t1) % 65521ull);
+                const uint32_t b = (uint32_t)(((unsigned long long)o + t2) % 65521ull);
+                if (((b << 16) | a) != r.w) stt = HDLZ_ST_BAD_ADLER;
+            }
         }
-        if (lane == 0) {
+        if (tid == 0) {
             out_len[sid] = stt == HDLZ_OK ? o : 0;
             if (status) status[sid] = stt;
         }
-        __syncwarp();
     }
 }
 
@@ -634,8 +795,8 @@ int launch_inflate_split(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_i
     uint4 *rec = reinterpret_cast<uint4 *>(pool);
     uint32_t *tokbuf = reinterpret_cast<uint32_t *>(rec + max_items);
     uint32_t *litbuf = tokbuf + (size_t)max_items * tokcap;
-    const size_t dec_smem = (size_t)kDecWarps * kTabEntries * 64;
-    const size_t res_smem = (size_t)kResWarps * kWinBytes;
+    const size_t dec_smem = (size_t)kDecWarps * (kTabEntries * 64 + 1024);
+    const size_t res_smem = (size_t)kWinBytes + kBitmapBytes;
     if (!ctx->split_attr_set) {
         HDLZ_CUDA(cudaFuncSetAttribute(k_decode_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
         HDLZ_CUDA(cudaFuncSetAttribute(k_decode_tokens, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -648,7 +809,7 @@ int launch_inflate_split(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_i
         reinterpret_cast<SplitScratch *>(scratch), tokbuf, tokcap, litbuf, litw, rec, queues);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
-    k_resolve_tokens<<<(unsigned)(ctx->sm_count * kResCtasPerSm), kResWarps * 32, res_smem, s>>>(
+    k_resolve_tokens<<<(unsigned)(ctx->sm_count * kResCtasPerSm), kResThreads, res_smem, s>>>(
         d_items, d_item_count, max_items, tokbuf, tokcap, litbuf, litw, rec, d_out, out_stride, d_out_len, d_status,
         flags, queues + 1);
     ctx->launches++;
