@@ -509,70 +509,158 @@ def main():
 
     gather = None
     if dist:
-        # configs[4]: NCCL gather of the per-block stream lengths (the only exchange the path has); not in `value`
+        from hdl_deflate_b200 import sharding
+        # configs[4] "NCCL used only to broadcast inputs and gather outputs" (none of it is in `value`):
+        # (a) all_gather of the per-block stream lengths (every rank derives the packed offsets),
+        # (b) the streams themselves, PACKED on each rank (hdlz_pack_batch) and gathered on rank 0 — only real
+        #     stream bytes cross NVLink,
+        # (c) the inputs once: rank 0 generates all N shards and sends every rank its own.
+        def timed_ms(fn):
+            fn()                                     # first call: NCCL's lazy channel set-up
+            torch.cuda.synchronize()
+            dist.barrier()
+            g0 = torch.cuda.Event(enable_timing=True)
+            g1 = torch.cuda.Event(enable_timing=True)
+            g0.record()
+            r = fn()
+            g1.record()
+            torch.cuda.synchronize()
+            gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+            return float(gt.item()), r
         outs = [torch.empty_like(d_clen) for _ in range(world)]
+        len_ms, _ = timed_ms(lambda: dist.all_gather(outs, d_clen))
+        d_packed = torch.empty(n * ostride, dtype=torch.uint8, device=dev)
+        d_poff = torch.zeros(n, dtype=torch.int64, device=dev)
+        d_ptot = torch.zeros(1, dtype=torch.int64, device=dev)
+        eng.pack_batch(d_comp, ostride, d_clen, d_packed, d_poff, d_ptot, n, stream=stream)
         torch.cuda.synchronize()
-        g0 = torch.cuda.Event(enable_timing=True)
-        g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather(outs, d_clen)
-        g1.record()
-        torch.cuda.synchronize()
-        # second warm call timed (the first one includes NCCL's lazy channel set-up)
-        g0.record()
-        dist.all_gather(outs, d_clen)
-        g1.record()
-        torch.cuda.synchronize()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather = {"what": "NCCL all_gather of out_len (4 B per block, every rank gets all lengths -> packed offsets)",
-                  "ms": float(gt.item())}
+        my_total = int(d_ptot.item())
+        out_ms, res = timed_ms(lambda: sharding.gather_streams(d_packed[:my_total], d_clen, n * world, dst=0))
+        g_buf, g_off, g_len = res
+        gathered_bytes = int(((g_len.to(torch.int64) + 3) & ~3).sum())
+        ok = True
+        if rank == 0:
+            # rank 0's own shard must sit at the start of the gathered buffer, every stream where the offsets say
+            ok = bool(torch.equal(g_buf[:my_total], d_packed[:my_total])) and int(g_off[n - 1]) == int(d_poff[n - 1])
+            # and the gathered streams of ANOTHER rank must inflate to that rank's blocks (checked on a sample)
+            m = min(4096, n)
+            first = n * (world - 1)
+            d_chk = torch.empty(m * BLOCK, dtype=torch.uint8, device=dev)
+            d_cl = torch.zeros(m, dtype=torch.int32, device=dev)
+            d_cs = torch.zeros(m, dtype=torch.int32, device=dev)
+            eng.decompress_batch(g_buf, g_off[first:first + m].contiguous(), 0, g_len[first:first + m].contiguous(), d_chk,
+                                 BLOCK, BLOCK, d_cl, d_cs, m, flags=hz.F_VERIFY_ADLER, stream=stream)
+            d_ref = torch.empty(m * BLOCK, dtype=torch.uint8, device=dev)
+            eng.generate_blocks(d_ref, BLOCK, BLOCK, m, first_block=first, stream=stream)
+            torch.cuda.synchronize()
+            ok = ok and int(d_cs.abs().sum()) == 0 and bool(torch.equal(d_chk, d_ref))
+        del g_buf, d_packed
+        d_all = None
+        if rank == 0:
+            d_all = torch.empty((n * world, BLOCK), dtype=torch.uint8, device=dev)
+            eng.generate_blocks(d_all, BLOCK, BLOCK, n * world, first_block=0, stream=stream)
+            torch.cuda.synchronize()
+        d_recv = torch.empty((n, BLOCK), dtype=torch.uint8, device=dev)
+        in_ms, _ = timed_ms(lambda: sharding.scatter_blocks(d_all, n * world, BLOCK, src=0, out=d_recv))
+        same = torch.tensor([int(torch.equal(d_recv.view(-1), d_in))], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        del d_all, d_recv
+        torch.cuda.empty_cache()
+        gather = {"what": "NCCL: all_gather of out_len (4 B per block); packed streams of every rank gathered on rank 0 "
+                          "(hdlz_pack_batch + point-to-point, only stream bytes cross NVLink); inputs scattered from rank 0 once",
+                  "ms": len_ms, "outputs_ms": out_ms, "outputs_bytes": gathered_bytes,
+                  "outputs_gbps": gathered_bytes / (out_ms * 1e-3) / 1e9,
+                  "outputs_verified": bool(ok), "inputs_ms": in_ms, "inputs_bytes": n * world * BLOCK,
+                  "inputs_gbps": n * (world - 1) * BLOCK / (in_ms * 1e-3) / 1e9,
+                  "inputs_equal_local_generation": bool(int(same.item()))}
 
     # ---- e2e: the same step through the host-buffer C ABI (pinned host memory, copies timed), on
-    # every rank at the same time (the ranks share the host's PCIe / memory system), max over ranks
+    # every rank at the same time (the ranks share the host's PCIe / memory system), max over ranks.
+    # Two legs: (i) the two calls back to back on one context — each is bound by its larger PCIe direction
+    # while the other direction idles; (ii) the calls on two contexts from two host threads, a step's
+    # decompress working on the previous step's streams while the next batch is compressed: both directions
+    # of the link stay busy.  (ii) is what a host that pipelines its batches gets and is the reported value.
     e2e = None
     if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
+        import ctypes
         ne = min(args.e2e_blocks, n)
         h_in = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
         h_in.copy_(d_in.view(n, BLOCK)[:ne])
-        h_comp = torch.empty(ne * ostride, dtype=torch.uint8, pin_memory=True)       # packed streams land here
-        h_off = torch.zeros(ne, dtype=torch.int64, pin_memory=True)
+        h_comp = [torch.empty(ne * ostride, dtype=torch.uint8, pin_memory=True) for _ in range(2)]   # packed streams
+        h_off = [torch.zeros(ne, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+        h_clen = [torch.zeros(ne, dtype=torch.int32, pin_memory=True) for _ in range(2)]
         h_back = torch.empty((ne, BLOCK), dtype=torch.uint8, pin_memory=True)
-        h_clen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
         h_blen = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
-        h_st = torch.zeros(ne, dtype=torch.int32, pin_memory=True)
-        lib, ctx = eng._lib, eng._ctx
-        import ctypes
-        total = ctypes.c_uint64(0)
+        h_st = [torch.zeros(ne, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        eng2 = hz.Engine(local)                                  # the decompressing context
+        lib = eng._lib
+        total = [ctypes.c_uint64(0), ctypes.c_uint64(0)]
 
-        def e2e_step():
-            rc = lib.hdlz_compress_host_packed(ctx, h_in.data_ptr(), BLOCK, None, BLOCK, h_comp.data_ptr(),
-                                               ne * ostride, h_off.data_ptr(), h_clen.data_ptr(), h_st.data_ptr(), ne,
-                                               ctypes.byref(total))
+        def comp(k):
+            rc = lib.hdlz_compress_host_packed(eng._ctx, h_in.data_ptr(), BLOCK, None, BLOCK, h_comp[k].data_ptr(),
+                                               ne * ostride, h_off[k].data_ptr(), h_clen[k].data_ptr(),
+                                               h_st[0].data_ptr(), ne, ctypes.byref(total[k]))
             assert rc == 0, lib.hdlz_last_error()
-            rc = lib.hdlz_decompress_host(ctx, h_comp.data_ptr(), h_off.data_ptr(), 0, h_clen.data_ptr(),
-                                          h_back.data_ptr(), BLOCK, BLOCK, h_blen.data_ptr(), h_st.data_ptr(), ne, 0)
+
+        def decomp(k, ctx):
+            rc = lib.hdlz_decompress_host(ctx, h_comp[k].data_ptr(), h_off[k].data_ptr(), 0, h_clen[k].data_ptr(),
+                                          h_back.data_ptr(), BLOCK, BLOCK, h_blen.data_ptr(), h_st[1].data_ptr(), ne, 0)
             assert rc == 0, lib.hdlz_last_error()
-        e2e_step()
+
+        def sync_ranks():
+            if dist:
+                dist.barrier()
+
+        def max_ranks(t):
+            if not dist:
+                return t
+            tt = torch.tensor([t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        # (i) back to back
+        comp(0)
+        decomp(0, eng._ctx)
         assert torch.equal(h_back, h_in)
-        if dist:
-            dist.barrier()
+        sync_ranks()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            e2e_step()
-        te = (time.perf_counter() - t0) / args.e2e_steps
-        if dist:
-            tt = torch.tensor([te], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            te = float(tt.item())
-        pk = int(total.value)
+            comp(0)
+            decomp(0, eng._ctx)
+        te_seq = max_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        # (ii) overlapped: step k compresses into buffer k & 1 while buffer (k - 1) & 1 is decompressed
+        comp(1)
+        h_back.zero_()
+        pool = ThreadPoolExecutor(2)
+
+        def ostep(k):
+            fa = pool.submit(comp, k & 1)
+            fb = pool.submit(decomp, (k - 1) & 1, eng2._ctx)
+            fa.result()
+            fb.result()
+        ostep(0)
+        ostep(1)
+        assert torch.equal(h_back, h_in)
+        sync_ranks()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            ostep(k)
+        te = max_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        pool.shutdown()
+        assert torch.equal(h_back, h_in)
+        pk = int(total[0].value)
         h2d = ne * BLOCK + pk + (8 + 4) * ne                 # blocks; packed streams + offsets + lengths
         d2h = pk + (8 + 4 + 4) * ne + ne * BLOCK + (4 + 4) * ne
         e2e = {"value": 2 * ne * BLOCK * world / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "blocks_per_step_per_gpu": ne, "ms_per_step": te * 1e3,
-               "api": "hdlz_compress_host_packed + hdlz_decompress_host (pinned host buffers, packed streams, "
-                      "chunked 3-stream pipeline)",
+               "api": "hdlz_compress_host_packed on one context and hdlz_decompress_host on a second one, from two host "
+                      "threads: a step compresses its batch while the previous step's streams are decompressed (pinned "
+                      "host buffers, packed streams, chunked 3-stream pipelines); every step moves one full round trip",
+               "back_to_back": {"value": 2 * ne * BLOCK * world / te_seq / 1e9, "ms_per_step": te_seq * 1e3,
+                                "api": "the same two calls one after the other on one context"},
                "note": "all %d ranks concurrently, max over ranks" % world}
+        eng2.close()
         del h_in, h_comp, h_back
 
     if rank != 0:
@@ -614,6 +702,7 @@ def main():
     if gather:
         # kernel-only (`value`) and including the gather of the lengths
         gather["value_incl_gather"] = 2 * unc * K / ((t_total + K * gather["ms"]) * 1e-3) / 1e9
+        gather["value_incl_output_gather"] = 2 * unc * K / ((t_total + K * (gather["ms"] + gather["outputs_ms"])) * 1e-3) / 1e9
         line["gather"] = gather
     # the north star's read-only variant of the compress roofline: input bytes / time against the HBM rate
     line["roofline"]["compress_input_read_frac"] = (n * BLOCK / (t_c / K * 1e-3) / 1e9) / peak

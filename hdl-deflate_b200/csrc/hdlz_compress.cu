@@ -234,29 +234,41 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 // atomic OR into the table, not with MATCH.ANY: that instruction occupies the SM-wide
                 // ADU pipe for ~2 cycles per DISTINCT value among the 32 lanes (~40 cycles on this
                 // data, profiles/r01_ubench_match.txt) and made the whole kernel ADU-bound.
-                const int c0 = t0 > 0 ? -1 : 0;
+                // The atomic's return value holds the lanes of the same value that went before this one; only
+                // the lanes BELOW it matter for the mask, and when the hardware took the lanes in ascending
+                // order (checked every chunk) that is what it holds: no read-back of the entry.
                 const uint32_t lane_bit = 1u << lane;
-                uint32_t vnext = in_s[32 + 32 * c0 + lane];
-                for (int c = c0; c <= kChunks; ++c) {
+                // one chunk: c = -1 the last chunk of the previous tile (fills the table only), 0 .. kChunks - 1 the
+                // tile, kChunks the look-ahead chunk (masks only).  Adler-32 partial sums (CSTATIC / CHECKSUM,
+                // deflate.py:826-831, 884-897) ride along in the tile's chunks; bytes past the stream end are zero.
+                auto chunk = [&](const int c, auto store, auto sums) {
                     const int i = 32 * c + lane;                 // tile-relative position
-                    const uint32_t v = vnext;
-                    if (c < kChunks) vnext = in_s[32 + 32 * (c + 1) + lane];
+                    const uint32_t v = in_s[32 + i];
                     const uint32_t mprev = T[v];
                     __syncwarp();
                     T[vprev] = 0;
                     __syncwarp();
-                    atomicOr(&T[v], lane_bit);
+                    uint32_t mcur = atomicOr(&T[v], lane_bit);
                     __syncwarp();
-                    const uint32_t mcur = T[v];
+                    if (__any_sync(HDLZ_FULL_MASK, (mcur >> lane) != 0u)) mcur = T[v];   // a higher lane went first
                     vprev = v;
-                    if (c >= 0) {
-                        Rw[i + (i >> 5)] = __funnelshift_r(mprev, mcur, lane);   // bit k <=> distance 32 - k
-                        if (c < kChunks) {
-                            s1 += v;                             // bytes past the stream end are zero
-                            s2 += v * (n_tile - (uint32_t)i);
-                        }
+                    if (decltype(store)::value) Rw[i + (i >> 5)] = __funnelshift_r(mprev, mcur, lane);   // bit k <=> distance 32 - k
+                    if (decltype(sums)::value) {
+                        s1 += v;
+                        s2 += v * (n_tile - (uint32_t)i);
                     }
-                }
+                };
+                if (t0 > 0) chunk(-1, std::false_type(), std::false_type());
+#pragma unroll 2
+                for (int c = 0; c < kChunks; ++c) chunk(c, std::true_type(), std::true_type());
+                chunk(kChunks, std::true_type(), std::false_type());
+            }
+            {
+                // Adler-32 of the tile (deflate.py:826-831, 884-897), folded in now so that the sums die here
+                const uint32_t S1 = __reduce_add_sync(HDLZ_FULL_MASK, s1);
+                const uint32_t S2 = __reduce_add_sync(HDLZ_FULL_MASK, s2);
+                adler_b = (adler_b + n_tile * adler_a + S2) % 65521u;
+                adler_a = (adler_a + S1) % 65521u;
             }
             if (L - 2 < t0 + kTile + 32) {                   // R[q] = 0 for q >= L - 2
                 __syncwarp();                                // other lanes wrote these words in phase A
@@ -403,14 +415,6 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
             }
             __syncwarp();
-
-            // ---------------- Adler-32 of the tile -------------------------------------------------------
-            {
-                const uint32_t S1 = __reduce_add_sync(HDLZ_FULL_MASK, s1);
-                const uint32_t S2 = __reduce_add_sync(HDLZ_FULL_MASK, s2);
-                adler_b = (adler_b + n_tile * adler_a + S2) % 65521u;
-                adler_a = (adler_a + S1) % 65521u;
-            }
 
             // ---------------- flush ---------------------------------------------------------------------
             uint32_t total = lbit + tile_bits;

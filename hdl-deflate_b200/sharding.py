@@ -92,3 +92,30 @@ def broadcast_blocks(blocks, src=0, group=None):
     dist.broadcast(blocks, src=src, group=group)
     first, last = shard_range(blocks.shape[0], rank, world)
     return blocks[first:last]
+
+
+def scatter_blocks(all_blocks, n_total, stride, src=0, group=None, out=None):
+    """Rank `src` owns all input blocks (uint8 [n_total, stride] on its device; None elsewhere); every rank
+    receives exactly its contiguous shard (point-to-point over NVLink: each byte crosses one link once).
+    -> uint8 [shard, stride] on every rank (`out` if given)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    first, last = shard_range(n_total, rank, world)
+    if rank == src:
+        mine = all_blocks[first:last]
+        ops = []
+        for r in range(world):
+            a, b = shard_range(n_total, r, world)
+            if r != src and b > a:
+                ops.append(dist.P2POp(dist.isend, all_blocks[a:b].contiguous(), r, group))
+        if out is not None:
+            out.copy_(mine)
+            mine = out
+    else:
+        device = out.device if out is not None else torch.device("cpu")
+        mine = out if out is not None else torch.empty((last - first, stride), dtype=torch.uint8, device=device)
+        ops = [dist.P2POp(dist.irecv, mine, src, group)] if last > first else []
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return mine

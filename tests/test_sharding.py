@@ -41,6 +41,8 @@ def _worker(rank, world, port, n_total, q):
             blocks[i] = torch.frombuffer(bytearray(workload.block(i, 2048)), dtype=torch.uint8)
     mine = sharding.broadcast_blocks(blocks, src=0)
     assert mine.shape[0] == last - first and mine[0].numpy().tobytes() == workload.block(first, 2048)
+    mine2 = sharding.scatter_blocks(blocks if rank == 0 else None, n_total, 2048, src=0)
+    assert torch.equal(mine2, mine)
     all_len = sharding.gather_lengths(lens, n_total)
     off, total = sharding.packed_offsets(all_len)
     gathered, off2, all_len2 = sharding.gather_streams(packed, lens, n_total, dst=0)
