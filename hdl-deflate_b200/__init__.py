@@ -116,6 +116,16 @@ class Engine(object):
         self._check(self._lib.hdlz_set_match10(self._ctx, 1 if on else 0))
 
     @property
+    def fast(self):
+        """The reference's FAST switch (deflate.py:36-37): True = 32-byte window (default), False = the non-FAST
+        engine with CWINDOW = 256."""
+        return bool(self._lib.hdlz_get_fast(self._ctx))
+
+    @fast.setter
+    def fast(self, on):
+        self._check(self._lib.hdlz_set_fast(self._ctx, 1 if on else 0))
+
+    @property
     def container(self):
         """Framing the compressor writes around the deflate body: CONTAINER_ZLIB (the reference's,
         default), CONTAINER_RAW or CONTAINER_GZIP."""

@@ -22,6 +22,8 @@ SIGNATURES = {
     "hdlz_compress_bound": (u32, [u32]),
     "hdlz_set_match10": (cint, [vp, cint]),
     "hdlz_get_match10": (cint, [vp]),
+    "hdlz_set_fast": (cint, [vp, cint]),
+    "hdlz_get_fast": (cint, [vp]),
     "hdlz_set_container": (cint, [vp, cint]),
     "hdlz_get_container": (cint, [vp]),
     "hdlz_compress_bound_ex": (u32, [u32, cint]),

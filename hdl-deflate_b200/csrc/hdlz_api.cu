@@ -51,7 +51,7 @@ int grow_device(void **p, size_t *cap, size_t need)
 
 static int ensure_pipe(hdlz_ctx *ctx)
 {
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < kHostPipe; i++)
         if (!ctx->pipe[i]) {
             cudaError_t e = cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking);
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(pipe)");
@@ -102,7 +102,7 @@ static int check_lengths(const uint32_t *len, uint64_t n, uint64_t stride, bool 
 // error exit of a chunked pipeline: nothing may still be copying into the caller's buffers
 static int drain(hdlz_ctx *ctx, int rc)
 {
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < kHostPipe; i++)
         if (ctx->pipe[i]) cudaStreamSynchronize(ctx->pipe[i]);
     return rc;
 }
@@ -163,6 +163,7 @@ int hdlz_create(int device, hdlz_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->max_match = HDLZ_MAX_MATCH;
+    c->window = HDLZ_CWINDOW;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -181,7 +182,7 @@ int hdlz_destroy(hdlz_ctx *c)
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < kHostPipe; i++)
         if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_out) cudaFree(c->d_out);
@@ -213,6 +214,15 @@ int hdlz_set_match10(hdlz_ctx *ctx, int match10)
 }
 
 int hdlz_get_match10(hdlz_ctx *ctx) { return ctx && ctx->max_match == HDLZ_MAX_MATCH ? 1 : 0; }
+
+int hdlz_set_fast(hdlz_ctx *ctx, int fast)
+{
+    if (!ctx) return set_error(HDLZ_ERR_INVALID, "null context");
+    ctx->window = fast ? HDLZ_CWINDOW : HDLZ_CWINDOW_SLOW;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_get_fast(hdlz_ctx *ctx) { return ctx && ctx->window == HDLZ_CWINDOW_SLOW ? 0 : 1; }
 
 int hdlz_set_container(hdlz_ctx *ctx, int container)
 {
@@ -276,7 +286,7 @@ int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, con
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
-        cudaStream_t s = ctx->pipe[k % 3];
+        cudaStream_t s = ctx->pipe[k % kHostPipe];
         HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                   cudaMemcpyHostToDevice, s));
         if (in_len)
@@ -291,7 +301,7 @@ int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, con
         if (status)
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < 3; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    for (int i = 0; i < kHostPipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
     return HDLZ_SUCCESS;
 }
 
@@ -332,7 +342,10 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
-        cudaStream_t s = ctx->pipe[k % 3];
+        cudaStream_t s = ctx->pipe[k % kHostPipe];
+        // at most kHostPipe chunks are queued: a second call running beside this one (another context, another
+        // host thread) gets its copies into the copy engines' queues between ours instead of behind all of them
+        if (k >= kHostPipe) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
         if (in_off) {
             const uint64_t lo = (nchunks == 1 ? 0 : in_off[first]) & ~(uint64_t)15;
             const uint64_t hi = nchunks == 1 ? in_bytes : in_off[first + m - 1] + in_len[first + m - 1];
@@ -353,7 +366,7 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
         if (status)
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < 3; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    for (int i = 0; i < kHostPipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
     return HDLZ_SUCCESS;
 }
 
@@ -406,12 +419,13 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
     uint64_t *d_tot = d_off + n;
     uint64_t *h_tot = ctx->h_small;
     uint64_t base = 0;
-    // stage 1 (copy in, compress, pack, small copies out) of chunk c is enqueued two chunks ahead of
+    // stage 1 (copy in, compress, pack, small copies out) of chunk c is enqueued kLag chunks ahead of
     // stage 2 (packed bytes out), which needs the chunk's packed size on the host
-    for (uint64_t c = 0; c < nchunks + 2; ++c) {
+    constexpr uint64_t kLag = kHostPipe - 1;
+    for (uint64_t c = 0; c < nchunks + kLag; ++c) {
         if (c < nchunks) {
             const uint64_t first = c * chunk, m = n - first < chunk ? n - first : chunk;
-            cudaStream_t s = ctx->pipe[c % 3];
+            cudaStream_t s = ctx->pipe[c % kHostPipe];
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                       cudaMemcpyHostToDevice, s));
             if (in_len)
@@ -428,13 +442,13 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
             if (status)
                 HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         }
-        if (c >= 2) {
-            const uint64_t cc = c - 2, first = cc * chunk, m = n - first < chunk ? n - first : chunk;
-            cudaStream_t s = ctx->pipe[cc % 3];
+        if (c >= kLag) {
+            const uint64_t cc = c - kLag, first = cc * chunk, m = n - first < chunk ? n - first : chunk;
+            cudaStream_t s = ctx->pipe[cc % kHostPipe];
             HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
             const uint64_t tot = h_tot[cc];
             if (base + tot > out_cap) {
-                for (int i = 0; i < 3; i++) cudaStreamSynchronize(ctx->pipe[i]);
+                for (int i = 0; i < kHostPipe; i++) cudaStreamSynchronize(ctx->pipe[i]);
                 return set_error(HDLZ_ERR_INVALID, "packed output needs more than out_cap = %llu bytes",
                                  (unsigned long long)out_cap);
             }
@@ -443,7 +457,7 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
             base += tot;
         }
     }
-    for (int i = 0; i < 3; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    for (int i = 0; i < kHostPipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
     if (out_total) *out_total = base;
     return HDLZ_SUCCESS;
 }

@@ -19,6 +19,8 @@ struct hdlz_ctx {
     int sm_count;
     uint32_t container;  // hdlz_container written by the compressor
     uint32_t max_match;  // longest match of the compressor: 10 (MATCH10, default) or 5 (deflate.py:34-35)
+    uint32_t window;     // search window of the compressor: 32 (FAST, default) or 256 (FAST = False, deflate.py:56-59)
+    bool wide_attr_set;
     // scratch for the host-buffer entry points (grown on demand, reused)
     uint8_t *d_in;
     size_t d_in_cap;
@@ -50,7 +52,7 @@ struct hdlz_ctx {
     uint32_t *h_dyn_seen;  // pinned [3]: dynamic-block streams the slot's last launch saw -> sizes the pool of the next one
     bool split_attr_set;
     cudaStream_t stream;  // owned, used by the host-buffer entry points
-    cudaStream_t pipe[3];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls
+    cudaStream_t pipe[6];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls (kHostPipe)
     unsigned long long launches;
     // per-context launch state (was function-static: two contexts / threads raced on it)
     bool compress_attr_set;   // cudaFuncSetAttribute of k_compress done for this context's device
@@ -58,6 +60,7 @@ struct hdlz_ctx {
 };
 
 namespace hdlz {
+constexpr int kHostPipe = 6;   // chunks in flight in the *_host pipelines: deep enough that neither copy direction waits for the host
 // Makes the context's device current for one entry point and restores the caller's device on return
 // (an engine on GPU k must not change the calling thread's current device).
 struct DeviceGuard {
@@ -96,6 +99,9 @@ int cuda_fail(cudaError_t e, const char *what);
 int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                     uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
                     uint32_t *d_status, uint64_t n, cudaStream_t s);
+int launch_compress_wide(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                         uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
+                         uint32_t *d_status, uint64_t n, unsigned long long *queue, cudaStream_t s);
 int launch_inflate(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint64_t in_stride,
                    const uint32_t *d_in_len, uint8_t *d_out, uint64_t out_stride, uint32_t out_cap,
                    uint32_t *d_out_len, uint32_t *d_status, uint64_t n, uint32_t flags, int slot, cudaStream_t s);

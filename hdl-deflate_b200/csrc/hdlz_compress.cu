@@ -482,6 +482,15 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, kQueueSlots * sizeof(unsigned long long)));
     unsigned long long *queue = ctx->d_queue + (ctx->queue_seq++ & (kQueueSlots - 1));
     HDLZ_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    if (ctx->window == 256) {
+        // the reference's non-FAST configuration (CWINDOW = 256): hdlz_compress_wide.cu
+        const int rc = launch_compress_wide(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status,
+                                            n, queue, s);
+        if (rc) return rc;
+        if (ctx->container == HDLZ_CONTAINER_GZIP)
+            return launch_gzip_trailers(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, n, s);
+        return HDLZ_SUCCESS;
+    }
     if (ctx->max_match == 5)
         k_compress<5><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
                                                                                d_out, out_stride, d_out_len, d_status, n, queue,

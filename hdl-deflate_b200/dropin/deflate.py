@@ -28,8 +28,10 @@ from myhdl import always, block, Error
 IDLE, WRITE, READ, STARTC, STARTD = range(5)
 
 # feature flags of the reference (deflate.py:20-41): the configuration this engine implements.
-# MATCH10 may be set to False before a block is instantiated (as with the reference, where it is a
-# module global read at elaboration): the engine then stops matches at 5 bytes (deflate.py:913-924).
+# MATCH10 and FAST may be set to False before a block is instantiated (as with the reference, where they
+# are module globals read at elaboration): MATCH10 = False stops matches at 5 bytes (deflate.py:913-924),
+# FAST = False selects the non-FAST engine with CWINDOW = 256 (deflate.py:56-59, 996-1062) — set CWINDOW
+# = 256 with it, as the reference derives it.
 LOWLUT = False
 COMPRESS = True
 DECOMPRESS = True
@@ -86,6 +88,7 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
     lin = bytearray()              # bytes by full address since the last write at address 0
     st = {"isize": 0, "job": IDLE, "out": b""}
     match10 = bool(MATCH10)        # read at elaboration, like every configuration global of the reference
+    fast = bool(FAST)
 
     def run_job():
         data = bytes(lin[:st["isize"] + 1])
@@ -94,6 +97,8 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
             if st["job"] == STARTC:
                 if hasattr(eng, "match10"):
                     eng.match10 = match10
+                if hasattr(eng, "fast"):
+                    eng.fast = fast
                 return eng.compress(data)
             return eng.decompress(data)
         except ValueError as e:            # StreamError: non-zero hdlz_status

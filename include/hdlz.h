@@ -39,6 +39,7 @@ extern "C" {
 
 /* Engine constants the reference exports as module globals (deflate.py:56-89). */
 #define HDLZ_CWINDOW 32      /* search window, FAST (deflate.py:56-57)               */
+#define HDLZ_CWINDOW_SLOW 256 /* search window with FAST = False (deflate.py:58-59)  */
 #define HDLZ_MAX_MATCH 10    /* MATCH10 (deflate.py:34-35, 913-952)                  */
 #define HDLZ_MAX_MATCH_SHORT 5 /* MATCH10 = False: SEARCHF stops at 5 (deflate.py:913-924) */
 #define HDLZ_MIN_INPUT 5     /* engine idles while isize < 4 (deflate.py:429-432)    */
@@ -109,6 +110,14 @@ uint32_t hdlz_compress_bound(uint32_t len);
  * with the same setting (FAST = True, CWINDOW = 32). */
 int hdlz_set_match10(hdlz_ctx *ctx, int match10);
 int hdlz_get_match10(hdlz_ctx *ctx);
+
+/* The reference's module switch FAST (deflate.py:36-37, 56-59): non-zero (the default, and what the BASELINE
+ * configs use) is the 32-byte window with the parallel `matcher3` search; zero selects the non-FAST engine —
+ * CWINDOW = 256, SEARCH / SEARCH10 walking back from the nearest position (deflate.py:996-1062), distance
+ * codes up to 15 (`outcarry`, :875-880).  Output is bit-identical to deflate.py built with the same FAST and
+ * MATCH10 settings.  A slower second mode: the search is direct, not the mask formulation of the FAST kernel. */
+int hdlz_set_fast(hdlz_ctx *ctx, int fast);
+int hdlz_get_fast(hdlz_ctx *ctx);
 
 /* Container of every later compress call of the context (hdlz_container; default zlib, the
  * reference's).  The deflate body is the same bits in all three.  hdlz_compress_bound_ex is the

@@ -16,9 +16,10 @@ class OracleEngine(object):
     def __init__(self):
         self.jobs = []
         self.match10 = True
+        self.fast = True
 
     def compress(self, data):
-        st, out = hdlz_oracle.compress(data, maxlen=10 if self.match10 else 5)
+        st, out = hdlz_oracle.compress(data, cwindow=32 if self.fast else 256, maxlen=10 if self.match10 else 5)
         self.jobs.append(("C", len(data), len(out)))
         if st:
             raise OracleStreamError("status %d" % st)

@@ -3,10 +3,13 @@ import hashlib
 import os
 import zlib
 
+import random
+
 import numpy as np
 import pytest
 
 from conftest import load_golden, golden_input
+import hdl_deflate_b200 as hz
 from hdl_deflate_b200 import workload, compress_bound
 from oracle import hdlz_oracle
 
@@ -53,6 +56,61 @@ def test_match10_false_bit_exact(engine):
         assert not bst.any() and np.array_equal(back, arr)
     finally:
         engine.match10 = True
+    assert engine.compress(b"a" * 12).hex() == "789c4b8483c444001d9a048d"
+
+
+def test_fast_false_window256_bit_exact(engine):
+    """The reference's FAST = False configuration (CWINDOW = 256, deflate.py:56-59, 996-1062; distance codes up
+    to 15, :875-880) with both MATCH10 settings: fixtures produced by the executing reference, then ragged
+    batches (multi-tile streams included) against the oracle, every container, and back through the inflater."""
+    assert engine.fast
+    engine.fast = False
+    try:
+        assert not engine.fast
+        for c in load_golden("compress_golden_w256.json"):
+            engine.match10 = c["match10"]
+            got = engine.compress(golden_input(c))
+            assert len(got) == c["out_len"], c["name"]
+            assert hashlib.sha256(got).hexdigest() == c["out_sha256"], c["name"]
+        engine.match10 = True
+        rnd = random.Random(256)
+        n = 1200
+        lens = np.array([rnd.choice([5, 6, 31, 255, 256, 257, 300, 1023, 1024, 1025, 2048, 3000]) for _ in range(n)], dtype=np.uint32)
+        arr = np.zeros((n, 3008), dtype=np.uint8)
+        plains = []
+        for i in range(n):
+            L = int(lens[i])
+            kind = i % 4
+            if kind == 0:
+                d = workload.block(5000 + i, L)
+            elif kind == 1:
+                p = bytes(rnd.randrange(256) for _ in range(rnd.choice([33, 64, 100, 200, 256])))
+                d = (p * (L // len(p) + 1))[:L]
+            elif kind == 2:
+                d = bytes(rnd.choice(b"abcdefgh") for _ in range(L))
+            else:
+                d = bytes([rnd.randrange(256)]) * L
+            plains.append(d)
+            arr[i, :L] = np.frombuffer(d, dtype=np.uint8)
+        for maxlen in (10, 5):
+            engine.match10 = maxlen == 10
+            out, out_len, status = engine.compress_host(arr, lens)
+            assert not status.any()
+            for i in range(n):
+                st, want = hdlz_oracle.compress(plains[i], cwindow=256, maxlen=maxlen)
+                assert st == 0 and out[i, :out_len[i]].tobytes() == want, (maxlen, i, int(lens[i]))
+            back, back_len, bst = engine.decompress_host(out, out_len, 3008, flags=hz.F_VERIFY_ADLER)
+            assert not bst.any()
+            for i in range(n):
+                assert back[i, :back_len[i]].tobytes() == plains[i], i
+        engine.match10 = True
+        engine.container = hz.CONTAINER_GZIP
+        import gzip
+        assert gzip.decompress(engine.compress(plains[1])) == plains[1]
+    finally:
+        engine.container = hz.CONTAINER_ZLIB
+        engine.match10 = True
+        engine.fast = True
     assert engine.compress(b"a" * 12).hex() == "789c4b8483c444001d9a048d"
 
 

@@ -148,3 +148,25 @@ def test_unchanged_reference_unittest_drives_the_host_model():
     tail = (r.stdout + r.stderr)[-2000:]
     assert r.returncode == 0, tail
     assert "Ran 1 test" in tail and "OK" in tail, tail
+
+
+def test_fast_switch_is_read_at_elaboration():
+    """FAST is a module global of the reference (deflate.py:36-37) read when the block is built: False selects
+    the 256-byte window of the non-FAST engine."""
+    from port_driver import import_dropin
+    _, m = import_dropin()
+    base = bytes(range(7, 107))
+    data = (base * 5)[:450]                 # repeats at distance 100: invisible to the 32-byte window
+    m.FAST = False
+    try:
+        p = Port(OracleEngine())
+        p.pulse_reset()
+        slow = p.preload(p.m.STARTC, data)
+    finally:
+        m.FAST = True
+    p = Port(OracleEngine())
+    p.pulse_reset()
+    fast = p.preload(p.m.STARTC, data)
+    assert slow == hdlz_oracle.compress(data, cwindow=256)[1]
+    assert fast == hdlz_oracle.compress(data)[1]
+    assert len(slow) < len(fast) and zlib.decompress(slow) == data

@@ -40,6 +40,23 @@ def test_compress_restatement_matches_golden_match5():
     assert differs > 10            # the switch changes the streams
 
 
+def test_compress_restatement_matches_golden_window256():
+    """FAST = False (deflate.py:36-37, 56-59: CWINDOW = 256, SEARCH / SEARCH10, distance codes up to 15 with the
+    `outcarry` split): fixtures of oracle/make_golden_window256.py, both MATCH10 settings."""
+    cases = load_golden("compress_golden_w256.json")
+    assert len(cases) >= 50
+    far = 0
+    for c in cases:
+        data = golden_input(c)
+        st, out = hdlz_oracle.compress(data, cwindow=256, maxlen=10 if c["match10"] else 5)
+        assert st == 0
+        assert len(out) == c["out_len"], c["name"]
+        assert hashlib.sha256(out).hexdigest() == c["out_sha256"], c["name"]
+        assert zlib.decompress(out) == data
+        far += len(out) < len(hdlz_oracle.compress(data, maxlen=10 if c["match10"] else 5)[1])
+    assert far > 10                # the wider window finds matches the FAST engine cannot
+
+
 def test_tuned_cpu_arm_equals_the_restatement():
     """hdlz_oracle_compress_fast (the CPU baseline bench.py times) must produce the restatement's bytes:
     golden vectors of both MATCH10 settings plus seeded fuzz around the 32-byte window edge."""
