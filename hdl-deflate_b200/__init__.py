@@ -248,8 +248,56 @@ class Engine(object):
         self._check(self._lib.hdlz_generate_blocks(self._ctx, _ptr(d_out), stride, length, n, seed, first_block,
                                                    stream or None))
 
+    def compress_stream(self):
+        """A CompressStream on this engine."""
+        return CompressStream(self)
+
     def sync(self, stream=0):
         self._check(self._lib.hdlz_stream_sync(self._ctx, stream or None))
+
+
+class CompressStream(object):
+    """One compress stream fed in pieces (hdlz_cstream_*): the port protocol's WRITE ... WRITE ... IDLE with the
+    engine running alongside (deflate.py:459-461, 768).  feed() returns the stream bytes completed so far,
+    finish() the rest; joined they equal Engine.compress() of the whole input."""
+
+    def __init__(self, engine):
+        self._eng = engine
+        self._lib = engine._lib
+        self._st = ctypes.c_void_p()
+        engine._check(self._lib.hdlz_cstream_begin(engine._ctx, ctypes.byref(self._st)))
+        self.in_progress = 0           # input position up to which the stream is encoded (o_iprogress)
+
+    def feed(self, data):
+        data = bytes(data)
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
+        cap = compress_bound(len(data) + 2048)
+        out = np.empty(cap, dtype=np.uint8)
+        n, prog = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._eng._check(self._lib.hdlz_cstream_feed(self._st, src.ctypes.data, len(data), out.ctypes.data, cap,
+                                                     ctypes.byref(n), ctypes.byref(prog)))
+        self.in_progress = int(prog.value)
+        return out[:n.value].tobytes()
+
+    def finish(self):
+        cap = compress_bound((1 << 20) + 8192)
+        out = np.empty(cap, dtype=np.uint8)
+        n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._eng._check(self._lib.hdlz_cstream_finish(self._st, out.ctypes.data, cap, ctypes.byref(n), ctypes.byref(st)))
+        if st.value:
+            raise StreamError(st.value)
+        return out[:n.value].tobytes()
+
+    def close(self):
+        if self._st.value:
+            self._lib.hdlz_cstream_end(self._st)
+            self._st = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default_engine = None

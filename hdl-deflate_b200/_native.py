@@ -36,6 +36,10 @@ SIGNATURES = {
                                          ctypes.POINTER(u64)]),
     "hdlz_compress_stream": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "hdlz_decompress_stream": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), u32]),
+    "hdlz_cstream_begin": (cint, [vp, ctypes.POINTER(vp)]),
+    "hdlz_cstream_feed": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
+    "hdlz_cstream_finish": (cint, [vp, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
+    "hdlz_cstream_end": (cint, [vp]),
     "hdlz_dev_alloc": (cint, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
     "hdlz_dev_free": (cint, [vp, vp]),
     "hdlz_host_alloc_pinned": (cint, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),

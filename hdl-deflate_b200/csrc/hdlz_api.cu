@@ -521,6 +521,161 @@ int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8
     return HDLZ_SUCCESS;
 }
 
+// ---- compress stream fed in pieces (see include/hdlz.h) -------------------------------------------------
+struct hdlz_cstream {
+    hdlz_ctx *ctx;
+    uint8_t *d_buf[2];        // input window on the device, ping-pong: bytes [base, received) of the stream
+    int cur;
+    uint32_t base;            // stream position of d_buf[cur][0] (a multiple of 16)
+    uint32_t received;        // stream bytes fed so far
+    uint32_t t0;              // next tile to encode (mirror of the device state)
+    uint8_t *d_out;           // output of one launch
+    uint32_t *d_small;        // out_len | status
+    hdlz::StreamCtl *d_ctl;
+    unsigned long long *d_queue;
+    hdlz::StreamCtl h_ctl;
+    bool finished;
+};
+
+namespace {
+constexpr uint32_t kCsTile = 1024;                      // tile of k_compress
+constexpr uint32_t kCsBuf = (1u << 20) + 4096;          // input window: a piece of up to 1 MiB per launch
+constexpr uint32_t kCsOut = (kCsBuf / 8) * 9 + 4096;    // nine bits per input byte at most
+
+int cstream_run(hdlz_cstream *st, bool closing, uint8_t *out, uint32_t out_cap, uint32_t *produced)
+{
+    hdlz_ctx *ctx = st->ctx;
+    cudaStream_t s = ctx->stream;
+    // tiles whose result no later byte can change: every `di < isize - k` guard of a position in the tile is
+    // decided once 34 bytes past the tile have arrived (deflate.py:913-952, 975-977)
+    uint32_t t_end = st->t0;
+    if (!closing) {
+        if (st->received >= kCsTile + 34u) t_end = (st->received - 34u) / kCsTile * kCsTile;
+        if (t_end <= st->t0) return HDLZ_SUCCESS;
+    }
+    st->h_ctl.t0 = st->t0;
+    st->h_ctl.t_end = t_end;
+    st->h_ctl.final = closing ? 1u : 0u;
+    st->h_ctl.out_words = 0;
+    HDLZ_CUDA(cudaMemcpyAsync(st->d_ctl, &st->h_ctl, sizeof(hdlz::StreamCtl), cudaMemcpyHostToDevice, s));
+    HDLZ_CUDA(cudaMemsetAsync(st->d_queue, 0, sizeof(unsigned long long), s));
+    HDLZ_CUDA(cudaMemsetAsync(st->d_small, 0, 2 * sizeof(uint32_t), s));
+    int rc = launch_compress_stream(ctx, st->d_buf[st->cur] - st->base, st->received, st->d_out, st->d_small, st->d_small + 1,
+                                    st->d_ctl, st->d_queue, s);
+    if (rc) return rc;
+    uint32_t small[2] = {0, 0};
+    HDLZ_CUDA(cudaMemcpyAsync(&st->h_ctl, st->d_ctl, sizeof(hdlz::StreamCtl), cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaMemcpyAsync(small, st->d_small, sizeof small, cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaStreamSynchronize(s));
+    const uint32_t nbytes = closing ? small[0] : 4u * st->h_ctl.out_words;
+    if (nbytes > out_cap) return set_error(HDLZ_ERR_INVALID, "stream output needs %u bytes, out_cap is %u", nbytes, out_cap);
+    if (nbytes) HDLZ_CUDA(cudaMemcpyAsync(out, st->d_out, nbytes, cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA(cudaStreamSynchronize(s));
+    *produced = nbytes;
+    if (!closing) {
+        st->t0 = t_end;
+        // slide the window: keep the 32 bytes before the next tile (the search window, deflate.py:442-453)
+        const uint32_t nb = (st->t0 - 32u) & ~15u;
+        if (nb > st->base) {
+            HDLZ_CUDA(cudaMemcpyAsync(st->d_buf[st->cur ^ 1], st->d_buf[st->cur] + (nb - st->base), st->received - nb,
+                                      cudaMemcpyDeviceToDevice, s));
+            st->cur ^= 1;
+            st->base = nb;
+        }
+    }
+    return HDLZ_SUCCESS;
+}
+}  // namespace
+
+int hdlz_cstream_begin(hdlz_ctx *ctx, hdlz_cstream **out)
+{
+    HDLZ_ENTER(ctx);
+    if (!out) return set_error(HDLZ_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (ctx->container == HDLZ_CONTAINER_GZIP)
+        return set_error(HDLZ_ERR_INVALID, "streams fed in pieces write the zlib or the raw container (the gzip CRC-32 is taken over the whole input)");
+    if (ctx->window != HDLZ_CWINDOW) return set_error(HDLZ_ERR_INVALID, "streams fed in pieces use the FAST engine (CWINDOW = 32)");
+    hdlz_cstream *st = new hdlz_cstream();
+    memset(st, 0, sizeof *st);
+    st->ctx = ctx;
+    cudaError_t e = cudaMalloc((void **)&st->d_buf[0], kCsBuf + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_buf[1], kCsBuf + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_out, kCsOut);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_small, 16);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_ctl, sizeof(hdlz::StreamCtl));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_queue, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        hdlz_cstream_end(st);
+        return cuda_fail(e, "cudaMalloc(stream)");
+    }
+    *out = st;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_cstream_feed(hdlz_cstream *st, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap, uint32_t *out_len,
+                      uint32_t *in_progress)
+{
+    if (!st) return set_error(HDLZ_ERR_INVALID, "null stream");
+    HDLZ_ENTER(st->ctx);
+    if ((!in && len) || !out_len || (!out && out_cap)) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (st->finished) return set_error(HDLZ_ERR_INVALID, "stream already finished");
+    if ((uint64_t)st->received + len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
+    *out_len = 0;
+    uint32_t done = 0;
+    while (done < len) {
+        // as much of the piece as the window holds, then everything that has become final
+        const uint32_t room = kCsBuf - (st->received - st->base);
+        const uint32_t n = len - done < room ? len - done : room;
+        HDLZ_CUDA(cudaMemcpyAsync(st->d_buf[st->cur] + (st->received - st->base), in + done, n, cudaMemcpyHostToDevice,
+                                  st->ctx->stream));
+        st->received += n;
+        done += n;
+        uint32_t produced = 0;
+        rc = cstream_run(st, false, out + *out_len, out_cap - *out_len, &produced);
+        if (rc) return rc;
+        *out_len += produced;
+    }
+    HDLZ_CUDA(cudaStreamSynchronize(st->ctx->stream));       // `in` may be reused by the caller
+    if (in_progress) *in_progress = st->t0;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_cstream_finish(hdlz_cstream *st, uint8_t *out, uint32_t out_cap, uint32_t *out_len, uint32_t *status)
+{
+    if (!st) return set_error(HDLZ_ERR_INVALID, "null stream");
+    HDLZ_ENTER(st->ctx);
+    if (!out_len || (!out && out_cap)) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (st->finished) return set_error(HDLZ_ERR_INVALID, "stream already finished");
+    *out_len = 0;
+    st->finished = true;
+    if (st->received < HDLZ_MIN_INPUT) {                       // the reference never starts (deflate.py:429-432)
+        if (status) *status = HDLZ_ST_SHORT_INPUT;
+        return HDLZ_SUCCESS;
+    }
+    uint32_t produced = 0;
+    rc = cstream_run(st, true, out, out_cap, &produced);
+    if (rc) return rc;
+    *out_len = produced;
+    if (status) *status = HDLZ_OK;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_cstream_end(hdlz_cstream *st)
+{
+    if (!st) return HDLZ_SUCCESS;
+    DeviceGuard guard;
+    guard.enter(st->ctx->device);
+    cudaStreamSynchronize(st->ctx->stream);
+    for (int i = 0; i < 2; i++)
+        if (st->d_buf[i]) cudaFree(st->d_buf[i]);
+    if (st->d_out) cudaFree(st->d_out);
+    if (st->d_small) cudaFree(st->d_small);
+    if (st->d_ctl) cudaFree(st->d_ctl);
+    if (st->d_queue) cudaFree(st->d_queue);
+    delete st;
+    return HDLZ_SUCCESS;
+}
+
 int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr)
 {
     HDLZ_ENTER(ctx);

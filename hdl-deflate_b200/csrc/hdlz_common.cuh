@@ -21,6 +21,7 @@ struct hdlz_ctx {
     uint32_t max_match;  // longest match of the compressor: 10 (MATCH10, default) or 5 (deflate.py:34-35)
     uint32_t window;     // search window of the compressor: 32 (FAST, default) or 256 (FAST = False, deflate.py:56-59)
     bool wide_attr_set;
+    bool stream_attr_set;
     // scratch for the host-buffer entry points (grown on demand, reused)
     uint8_t *d_in;
     size_t d_in_cap;
@@ -84,6 +85,17 @@ struct DeviceGuard {
 }  // namespace hdlz
 
 namespace hdlz {
+
+// what a compress stream carries from one launch to the next (device memory; see k_compress<.., true>)
+struct StreamCtl {
+    uint32_t t0;        // next position to process (a multiple of the tile size)
+    uint32_t t_end;     // this launch stops here (not used by the closing launch)
+    uint32_t final;     // closing launch: `received` is the stream's true length
+    uint32_t carry, adler_a, adler_b, pw, lbit;
+    uint32_t out_words; // 32-bit words this launch wrote (the closing launch reports bytes through out_len)
+};
+int launch_compress_stream(hdlz_ctx *ctx, const uint8_t *d_in_virtual, uint32_t received, uint8_t *d_out, uint32_t *d_out_len,
+                           uint32_t *d_status, StreamCtl *d_ctl, unsigned long long *d_queue, cudaStream_t s);
 
 // error plumbing (hdlz_api.cu)
 int set_error(int code, const char *fmt, ...);

@@ -136,11 +136,18 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 }
 
 // kMaxMatch: 10 = the reference's MATCH10 configuration, 5 = MATCH10 False (deflate.py:34-35, 913-924)
-template <int kMaxMatch>
+// kStream: one stream fed in pieces (hdlz_stream_*): the launch works on the tiles [ctl->t0, ctl->t_end) of a
+// stream whose first `uniform_len` bytes have arrived, resumes from and saves to *ctl what the reference's FSM
+// keeps between clocks — bit cursor and partial output word (`do` / `doo` / `ob1`, deflate.py:535-567), the parse
+// position (`di`), both Adler sums — and writes the words it completes to out[0 ..]; `in` is the address the
+// stream's byte 0 would have (only bytes from t0 - 32 on are read).  The last launch (ctl->final) knows the true
+// length and closes the stream.  Compiled out of the batch kernel.
+template <int kMaxMatch, bool kStream>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len,
            uint32_t uniform_len, uint8_t *__restrict__ out, uint64_t out_stride,
-           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue, uint32_t container)
+           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue,
+           uint32_t container, StreamCtl *ctl)
 {
     extern __shared__ uint4 smem_raw[];
     uint32_t *LT = reinterpret_cast<uint32_t *>(smem_raw);
@@ -173,7 +180,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         const uint32_t L = in_len ? in_len[sid] : uniform_len;
         const uint8_t *src = in + sid * in_stride;
         uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + sid * out_stride);
-        if (L < HDLZ_MIN_INPUT || (uint64_t)compress_bound(L, container) > out_stride) {
+        if (!kStream && (L < HDLZ_MIN_INPUT || (uint64_t)compress_bound(L, container) > out_stride)) {
             if (lane == 0) {
                 out_len[sid] = 0;
                 if (status) status[sid] = L < HDLZ_MIN_INPUT ? HDLZ_ST_SHORT_INPUT : HDLZ_ST_OUT_OVERFLOW;
@@ -201,8 +208,23 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             wbase = 2;
         }
 
-        for (uint32_t t0 = 0; t0 < L; t0 += kTile) {
-            const bool last_tile = t0 + kTile >= L;
+        uint32_t t_first = 0, t_stop = L;
+        bool closing = true;             // this launch reaches the end of the stream
+        if (kStream) {
+            t_first = ctl->t0;
+            closing = ctl->final != 0;
+            if (!closing) t_stop = ctl->t_end;
+            if (t_first != 0) {          // resume: the state the previous launch left
+                carry = ctl->carry;
+                adler_a = ctl->adler_a;
+                adler_b = ctl->adler_b;
+                pw = ctl->pw;
+                lbit = ctl->lbit;
+                wbase = 0;
+            }
+        }
+        for (uint32_t t0 = t_first; t0 < t_stop; t0 += kTile) {
+            const bool last_tile = closing && t0 + kTile >= L;
             const uint32_t n_tile = last_tile ? L - t0 : kTile;
 
             // ---------------- load: HBM -> shared, 128-bit cp.async where the vector is inside the stream
@@ -454,11 +476,45 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
             }
         }
+        if (kStream) {
+            __syncwarp();
+            if (lane == 0) {
+                if (!closing) {
+                    ctl->t0 = t_stop;
+                    ctl->carry = carry;
+                    ctl->adler_a = adler_a;
+                    ctl->adler_b = adler_b;
+                    ctl->pw = pw;
+                    ctl->lbit = lbit;
+                }
+                ctl->out_words = wbase;
+            }
+        }
         sid = n_warps + __shfl_sync(HDLZ_FULL_MASK, next_ticket, 0);
     }
 }
 
 }  // namespace
+
+// One launch of the stream kernel (hdlz_stream_feed / hdlz_stream_finish, hdlz_api.cu): a single warp.
+int launch_compress_stream(hdlz_ctx *ctx, const uint8_t *d_in_virtual, uint32_t received, uint8_t *d_out, uint32_t *d_out_len,
+                           uint32_t *d_status, StreamCtl *d_ctl, unsigned long long *d_queue, cudaStream_t s)
+{
+    if (!ctx->stream_attr_set) {
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        ctx->stream_attr_set = true;
+    }
+    if (ctx->max_match == 5)
+        k_compress<5, true><<<1, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status,
+                                                                      1, d_queue, ctx->container, d_ctl);
+    else
+        k_compress<10, true><<<1, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status,
+                                                                       1, d_queue, ctx->container, d_ctl);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
 
 int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                     uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
@@ -466,10 +522,10 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
 {
     if (n == 0) return HDLZ_SUCCESS;
     if (!ctx->compress_attr_set) {
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         ctx->compress_attr_set = true;
     }
     uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -492,13 +548,13 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
         return HDLZ_SUCCESS;
     }
     if (ctx->max_match == 5)
-        k_compress<5><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
+        k_compress<5, false><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
                                                                                d_out, out_stride, d_out_len, d_status, n, queue,
-                                                                               ctx->container);
+                                                                               ctx->container, nullptr);
     else
-        k_compress<10><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
+        k_compress<10, false><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
                                                                                 d_out, out_stride, d_out_len, d_status, n, queue,
-                                                                                ctx->container);
+                                                                                ctx->container, nullptr);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     if (ctx->container == HDLZ_CONTAINER_GZIP)

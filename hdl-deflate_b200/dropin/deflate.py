@@ -86,14 +86,39 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
 
     ring = bytearray(IBSIZE)       # mirror of iram: what a byte address holds if never rewritten
     lin = bytearray()              # bytes by full address since the last write at address 0
-    st = {"isize": 0, "job": IDLE, "out": b""}
+    st = {"isize": 0, "job": IDLE, "out": b"", "stream": None, "fed": 0}
     match10 = bool(MATCH10)        # read at elaboration, like every configuration global of the reference
     fast = bool(FAST)
+
+    def feed_stream():
+        """STARTC with input still arriving (the UnitTest flow, test_deflate.py:216-260): every IBSIZE bytes the
+        host has written in order go to the engine's stream (hdlz_cstream_feed) while it keeps writing — the
+        reference consumes its iram the same way (deflate.py:459-461, 768) — and the stream bytes completed so
+        far become readable: o_oprogress follows the engine's real output, as it does in the reference."""
+        eng = _get_backend()
+        if st["stream"] is None:
+            if not fast or not hasattr(eng, "compress_stream") or getattr(eng, "container", 0) == 2:
+                return
+            if hasattr(eng, "match10"):
+                eng.match10 = match10
+            if hasattr(eng, "fast"):
+                eng.fast = True
+            st["stream"] = eng.compress_stream()
+            st["out"] = b""
+        piece = bytes(lin[st["fed"]:st["fed"] + IBSIZE])
+        st["fed"] += IBSIZE
+        st["out"] = st["out"] + st["stream"].feed(piece)
 
     def run_job():
         data = bytes(lin[:st["isize"] + 1])
         eng = _get_backend()
         try:
+            if st["job"] == STARTC and st["stream"] is not None:
+                stream, st["stream"] = st["stream"], None
+                try:
+                    return st["out"] + stream.feed(data[st["fed"]:]) + stream.finish()
+                finally:
+                    stream.close()
             if st["job"] == STARTC:
                 if hasattr(eng, "match10"):
                     eng.match10 = match10
@@ -133,6 +158,10 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
         elif st["job"] == IDLE:
             if mode == STARTC or mode == STARTD:
                 st["job"] = mode
+                st["fed"] = 0
+                if st["stream"] is not None:
+                    st["stream"].close()
+                    st["stream"] = None
                 o_done.next = False
                 o_iprogress.next = 0
                 o_oprogress.next = 0
@@ -149,5 +178,15 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
                 else:
                     slack = 10 if st["job"] == STARTC else 4
                     o_iprogress.next = isize - slack if isize > slack else 0
+                    # bytes written in order since the START, a whole IBSIZE of them beyond what the engine has
+                    # (plus its 32-byte look-ahead): hand them over while the host keeps writing
+                    if st["job"] == STARTC and mode == WRITE and int(i_waddr) == isize and \
+                            isize + 1 - st["fed"] >= IBSIZE + 2 * CWINDOW:
+                        try:
+                            feed_stream()
+                        except ValueError as e:
+                            raise Error(str(e).split(" (")[0])
+                        if st["stream"] is not None:
+                            o_oprogress.next = len(st["out"])
 
     return port

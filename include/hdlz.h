@@ -180,6 +180,26 @@ int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t
 int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
                            uint32_t *out_len, uint32_t *status, uint32_t flags);
 
+/* ---- one stream fed in pieces --------------------------------------------
+ * The port protocol streams: the host WRITEs input while the engine runs, and the engine stalls at
+ * `di >= isize - 10` until more bytes arrive or IDLE says there are none (deflate.py:459-461, 768; flow
+ * control of the test bench, test_deflate.py:159, 250).  hdlz_cstream_* is that for the compressor: feed any
+ * number of pieces of any size, collect the stream bytes as they are completed; the engine carries the bit
+ * cursor and partial output word (`do` / `doo` / `ob1`), the parse position, the last 32 bytes and both
+ * Adler sums from call to call (state lives on the device).  The concatenated output is bit-identical to
+ * one hdlz_compress_stream call over the whole input (and so to deflate.py).  zlib and raw containers.
+ *   feed:   consumes all of `in`; writes the bytes completed so far to out (at most out_cap; size it
+ *           hdlz_compress_bound(len + 2048)), *out_len their count, *in_progress the input position up to
+ *           which the stream is encoded (the reference's o_iprogress).
+ *   finish: no more input (the reference's IDLE after START): the rest of the stream, EOB, Adler-32.
+ *           *status as hdlz_compress_stream (HDLZ_ST_SHORT_INPUT for fewer than 5 bytes in total). */
+typedef struct hdlz_cstream hdlz_cstream;
+int hdlz_cstream_begin(hdlz_ctx *ctx, hdlz_cstream **stream);
+int hdlz_cstream_feed(hdlz_cstream *stream, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                      uint32_t *out_len, uint32_t *in_progress);
+int hdlz_cstream_finish(hdlz_cstream *stream, uint8_t *out, uint32_t out_cap, uint32_t *out_len, uint32_t *status);
+int hdlz_cstream_end(hdlz_cstream *stream);
+
 /* ---- device memory helpers (for hosts without their own CUDA allocator) --- */
 int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr);
 int hdlz_dev_free(hdlz_ctx *ctx, void *d_ptr);

@@ -318,3 +318,53 @@ def test_full_size_properties(engine):
     assert int(d_bst.abs().sum()) == 0
     assert bool((d_blen == L).all())
     assert torch.equal(d_back, d_in)
+
+
+def test_stream_fed_in_pieces(engine):
+    """hdlz_cstream_*: a stream fed in pieces — 1 MB in 2 KiB pieces, ragged piece sizes, tiny streams — gives
+    exactly the bytes of the one-shot call (and so of deflate.py): the state the reference keeps between clocks
+    (bit cursor, partial word, parse position, 32-byte window, Adler sums) survives from call to call."""
+    rnd = random.Random(4242)
+    big = b"".join(workload.blocks(7000, 512, 2048))                   # 1 MiB
+    want = hdlz_oracle.compress(big)[1]
+    s = engine.compress_stream()
+    got = bytearray()
+    progress = 0
+    for i in range(0, len(big), 2048):
+        got += s.feed(big[i:i + 2048])
+        assert progress <= s.in_progress <= i + 2048                     # o_iprogress never runs ahead of the input
+        progress = s.in_progress
+    assert progress > len(big) - 8192                                    # and follows it closely
+    assert len(got) > 0.9 * len(want)                                    # most of the stream was out before finish()
+    got += s.finish()
+    s.close()
+    assert bytes(got) == want
+    assert engine.compress(big) == want                                  # one-shot call: the same bytes
+    for trial in range(40):
+        L = rnd.choice([0, 3, 5, 6, 40, 1023, 1024, 1025, 1057, 1058, 1059, 2048, 2081, 2082, 2083, 5000, 70000])
+        data = workload.block(8000 + trial, max(L, 1))[:L] if trial % 3 else bytes(rnd.choice(b"ab") for _ in range(L))
+        s = engine.compress_stream()
+        got, pos = bytearray(), 0
+        while pos < L:
+            n = rnd.choice([1, 2, 7, 33, 100, 1024, 1100, 4096, 20000])
+            got += s.feed(data[pos:pos + n])
+            pos += n
+        if L < 5:
+            with pytest.raises(hz.StreamError) as e:
+                s.finish()
+            assert e.value.status == 1                                   # SHORT_INPUT: the reference never starts
+        else:
+            got += s.finish()
+            assert bytes(got) == hdlz_oracle.compress(data)[1], (trial, L)
+        s.close()
+    engine.match10 = False
+    engine.container = hz.CONTAINER_RAW
+    try:
+        s = engine.compress_stream()
+        data = big[:50000]
+        got = b"".join(s.feed(data[i:i + 3000]) for i in range(0, len(data), 3000)) + s.finish()
+        s.close()
+        assert got == hdlz_oracle.compress(data, maxlen=5)[1][2:-4]      # raw container: the same body
+    finally:
+        engine.match10 = True
+        engine.container = hz.CONTAINER_ZLIB
