@@ -274,12 +274,23 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         fill += 32;
         nextw = load_word(wi);
     };
+    // Adler-32 of m appended bytes (the low m bytes of v, the rest zero): a += S, b += m a + m S - sum j x_j with
+    // two dot products per word; the modulo is deferred like zlib's (both sums stay below 2^32 for 5552 bytes)
     auto adler_bytes = [&](uint32_t v, uint32_t m) {
-        for (uint32_t k = 0; k < m; ++k) {
-            ad_a += (v >> (8u * k)) & 255u;
-            ad_b += ad_a;
-            if (++ad_n == 5552) { ad_a %= 65521u; ad_b %= 65521u; ad_n = 0; }
-        }
+        const uint32_t S = __dp4a(v, 0x01010101u, 0u), J = __dp4a(v, 0x03020100u, 0u);
+        ad_b += m * (ad_a + S) - J;
+        ad_a += S;
+        ad_n += m;
+        if (ad_n >= 5544u) { ad_a %= 65521u; ad_b %= 65521u; ad_n = 0; }
+    };
+    auto adler_bytes8 = [&](unsigned long long v, uint32_t m) {
+        const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        const uint32_t S = __dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, 0u));
+        const uint32_t J = __dp4a(lo, 0x03020100u, __dp4a(hi, 0x07060504u, 0u));
+        ad_b += m * (ad_a + S) - J;
+        ad_a += S;
+        ad_n += m;
+        if (ad_n >= 5544u) { ad_a %= 65521u; ad_b %= 65521u; ad_n = 0; }
     };
     // Store 32 completed bytes (two 128-bit stores = whole sectors) while this lane has them.
     // Called at converged points of the loop; `flushed` counts the words already in global memory.
@@ -352,10 +363,7 @@ k_inflate_lanes(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     // ... and appending the low m (1..8) bytes of v: three ring words are written back
     auto append8 = [&](unsigned long long v, uint32_t m) {
         v &= s_mask8[m];
-        if (want_adler) {
-            adler_bytes((uint32_t)v, m < 4u ? m : 4u);
-            if (m > 4u) adler_bytes((uint32_t)(v >> 32), m - 4u);
-        }
+        if (want_adler) adler_bytes8(v, m);
         const uint32_t ob = o & 3u, wo = o >> 2, sh = 8u * ob;
         const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
         const uint32_t wa = cw | (lo << sh);
