@@ -33,16 +33,15 @@
 namespace hdlz {
 namespace {
 
-constexpr int kDecWarps = 4;
+constexpr int kDecWarps = 5;
 constexpr int kDecCtasPerSm = 2;
 constexpr int kLitBits = 8;
 constexpr int kDistBits = 7;
-// per-lane table block, in 16-bit entries
-constexpr int kLitEnt0 = 0;                                   // 256 entries
-constexpr int kDistEnt0 = kLitEnt0 + (1 << kLitBits);         // 128 entries (also the 7-bit code-length-code table)
-constexpr int kCntLEnt0 = kDistEnt0 + (1 << kDistBits);       // 16 codes per length, literal/length code
-constexpr int kCntDEnt0 = kCntLEnt0 + 16;                     // 16, distance code (and the code-length code)
-constexpr int kTabEntries = kCntDEnt0 + 16;                   // 416 entries = 832 B per lane
+// per-warp table block: 256 16-bit literal/length entries and 128 8-bit distance entries per lane = 640 B per lane
+constexpr int kLitBytes = (1 << kLitBits) * 64;               // entry i of lane l at i * 64 + 2 l
+constexpr int kDistBytes = (1 << kDistBits) * 32;             // entry i of lane l at kLitBytes + i * 32 + l (also the code-length-code table)
+constexpr int kTabBytes = kLitBytes + kDistBytes;             // 20 KiB per warp
+constexpr int kRingBytes = 1024;                              // input ring: two 16-byte vectors per lane
 
 constexpr int kResThreads = 256;
 constexpr int kResCtasPerSm = 6;
@@ -58,35 +57,42 @@ __constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65
                                       257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193,
                                       12289, 16385, 24577};
 
-// 16-bit arrays of one lane inside the warp's table block: entry i of lane l sits at byte i * 64 + 2 * l
-// (one multiply-add to address; a bank serves two lanes, so a look-up costs at most two wavefronts)
+// The tables of one lane inside the warp's block.  Literal/length entries are (symbol << 4 | length), kLongCode for a
+// code longer than the table (and for an unused index); distance and code-length-code entries are bytes,
+// (symbol << 3 | length) with lengths 1..7, 0 for a longer code / unused index.  One multiply-add addresses either;
+// a bank serves two (four) lanes.
 struct LaneTab {
-    uint8_t *base;         // warp block + 2 * lane
-    __device__ __forceinline__ uint32_t get(int ent0, uint32_t idx) const
-    {
-        return *reinterpret_cast<const uint16_t *>(base + (size_t)(ent0 + idx) * 64u);
-    }
-    __device__ __forceinline__ void set(int ent0, uint32_t idx, uint32_t v) const
-    {
-        *reinterpret_cast<uint16_t *>(base + (size_t)(ent0 + idx) * 64u) = (uint16_t)v;
-    }
+    uint8_t *lit;          // warp block + 2 * lane
+    uint8_t *dist;         // warp block + kLitBytes + lane
+    __device__ __forceinline__ uint32_t get_lit(uint32_t idx) const { return *reinterpret_cast<const uint16_t *>(lit + idx * 64u); }
+    __device__ __forceinline__ void set_lit(uint32_t idx, uint32_t v) const { *reinterpret_cast<uint16_t *>(lit + idx * 64u) = (uint16_t)v; }
+    __device__ __forceinline__ uint32_t get_dist(uint32_t idx) const { return dist[idx * 32u]; }
+    __device__ __forceinline__ void set_dist(uint32_t idx, uint32_t v) const { dist[idx * 32u] = (uint8_t)v; }
 };
 
-constexpr uint32_t kLongCode = 0xF000u;     // table entry of a code longer than the table: not a literal, length 0
+constexpr uint32_t kLongCode = 0xF000u;     // literal/length entry of a code longer than the table: not a literal, length 0
 
-// Canonical Huffman tables of one code (HF1INIT..HF4, SPREAD; deflate.py:1227-1400), built by ONE thread:
-// primary table (symbol << 4 | length; kLongCode = longer code, also what an unused index holds) and count
-// array in its shared-memory block, sorted symbols and the resume point of the bit-serial decode in its
-// global scratch.  Returns 0, or 1 for an over-subscribed / illegally incomplete code (zlib's inflate_table rules).
-__device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t, int tent0, int tbits, int cent0,
-                                        uint16_t *sorted, uint16_t *resume, bool allow_incomplete)
+// Canonical Huffman tables of one code (HF1INIT..HF4, SPREAD; deflate.py:1227-1400), built by ONE thread: primary
+// table in its shared-memory block (kWide: the 16-bit literal/length table, else the 8-bit one), sorted symbols and
+// the resume point of the bit-serial decode in its global scratch, and — packed into 64 bits that stay in a
+// register — the number of codes of every length beyond the table (`cbits` bits each), which is all the bit-serial
+// decode needs.  Returns 0, 1 for an over-subscribed / illegally incomplete code (zlib's inflate_table rules), 3 for
+// a code without symbols where the caller wants one.
+template <bool kWide>
+__device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t, int tbits, int cbits, uint16_t *sorted,
+                                        uint16_t *resume, bool allow_incomplete, unsigned long long *beyond)
 {
     uint16_t cnt[16], first[16], offs[16], run[16];
     for (int l = 0; l < 16; ++l) { cnt[l] = 0; run[l] = 0; }
     for (int s = 0; s < nsym; ++s) cnt[lens[s]]++;
     cnt[0] = 0;
-    for (int l = 0; l < 16; ++l) t.set(cent0, l, cnt[l]);
-    for (int i = 0; i < (1 << tbits); ++i) t.set(tent0, i, kLongCode);
+    unsigned long long pk = 0;
+    for (int l = tbits + 1; l <= 15; ++l) pk |= (unsigned long long)cnt[l] << (cbits * (l - tbits - 1));
+    *beyond = pk;
+    for (int i = 0; i < (1 << tbits); ++i) {
+        if (kWide) t.set_lit(i, kLongCode);
+        else t.set_dist(i, 0);
+    }
     resume[0] = resume[1] = 0;
     int left = 1, maxlen = 0;
     for (int l = 1; l <= 15; ++l) {
@@ -95,7 +101,7 @@ __device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t
         if (c) maxlen = l;
         if (left < 0) return 1;
     }
-    if (maxlen == 0) return 0;                 // no codes: any use fails later
+    if (maxlen == 0) return 3;                 // no codes: any use fails later
     if (left > 0 && !(allow_incomplete && maxlen == 1)) return 1;
     uint32_t code = 0, off = 0;
     for (int l = 1; l <= 15; ++l) {
@@ -113,8 +119,10 @@ __device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t
         sorted[offs[l] + k] = (uint16_t)s;
         if ((int)l <= tbits) {
             const uint32_t rev = __brev(first[l] + k) >> (32 - l);
-            const uint32_t ent = ((uint32_t)s << 4) | l;
-            for (uint32_t idx = rev; idx < (1u << tbits); idx += 1u << l) t.set(tent0, idx, ent);
+            for (uint32_t idx = rev; idx < (1u << tbits); idx += 1u << l) {
+                if (kWide) t.set_lit(idx, ((uint32_t)s << 4) | l);
+                else t.set_dist(idx, ((uint32_t)s << 3) | l);
+            }
         }
     }
     return 0;
@@ -122,13 +130,13 @@ __device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t
 
 // code longer than the primary table: canonical decode one bit at a time, starting after the `tbits`
 // bits the table has already ruled out.  -> (sym << 4) | len, 0 = invalid
-__device__ __forceinline__ uint32_t split_slow(uint32_t bits, LaneTab t, int cent0, const uint16_t *sorted, int tbits,
-                                               const uint16_t *resume)
+__device__ __forceinline__ uint32_t split_slow(uint32_t bits, unsigned long long beyond, int cbits, const uint16_t *sorted,
+                                               int tbits, const uint16_t *resume)
 {
     int code = (int)((__brev(bits) >> (32 - tbits)) << 1), first = resume[0], index = resume[1];
     for (int l = tbits + 1; l <= 15; ++l) {
         code |= (int)((bits >> (l - 1)) & 1u);
-        const int c = (int)t.get(cent0, l);
+        const int c = (int)((beyond >> (cbits * (l - tbits - 1))) & ((1u << cbits) - 1u));
         if (code - c < first) return ((uint32_t)sorted[index + (code - first)] << 4) | (uint32_t)l;
         index += c;
         first += c;
@@ -155,7 +163,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 {
     const uint32_t n_items = min(*item_count, max_items);
     if (n_items == 0) return;
-    extern __shared__ uint32_t s_tab[];                     // [kDecWarps][kTabEntries][32 lanes] x u16, then the input rings
+    extern __shared__ uint32_t s_tab[];                     // [kDecWarps] table blocks, then the input rings
     __shared__ uint32_t s_len[32];                          // length symbol - 257 -> len_entry
     __shared__ uint32_t s_dsym[32];                         // distance symbol -> dist_entry
     if (threadIdx.x < 29) s_len[threadIdx.x] = len_entry(257 + threadIdx.x);
@@ -164,10 +172,12 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
 
     enum { S_IDLE = 0, S_HEADER = 1, S_BLOCK = 2, S_STORED = 3, S_FINISH = 4, S_DONE = 5 };
     const int lane = threadIdx.x & 31;
-    const LaneTab tab = {reinterpret_cast<uint8_t *>(s_tab) + (size_t)(threadIdx.x >> 5) * kTabEntries * 64 + 2 * lane};
+    uint8_t *wblock = reinterpret_cast<uint8_t *>(s_tab) + (size_t)(threadIdx.x >> 5) * kTabBytes;
+    const LaneTab tab = {wblock + 2 * lane, wblock + kLitBytes + lane};
+    unsigned long long beyond_l = 0, beyond_d = 0;          // codes per length beyond the tables (9..15 x 9 bits, 8..15 x 8 bits)
     SplitScratch *my = scratch + ((size_t)blockIdx.x * (kDecWarps * 32) + threadIdx.x);
     // input ring of this lane: two slots of four words; slot s at ring[s * 128 .. +4) (16 bytes per lane, 512 per slot)
-    uint32_t *ring = s_tab + (size_t)kDecWarps * kTabEntries * 16 + (size_t)(threadIdx.x >> 5) * 256 + 4 * lane;
+    uint32_t *ring = s_tab + (size_t)kDecWarps * (kTabBytes / 4) + (size_t)(threadIdx.x >> 5) * (kRingBytes / 4) + 4 * lane;
 
     const uint32_t trailer_bytes = (flags & HDLZ_F_RAW) ? 0u : (flags & HDLZ_F_GZIP) ? 8u : 4u;
     uint32_t state = S_IDLE;
@@ -311,7 +321,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     bool go = true;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const uint32_t e = tab.get(kLitEnt0, (x >> used) & ((1u << kLitBits) - 1u));
+                        const uint32_t e = tab.get_lit((x >> used) & ((1u << kLitBits) - 1u));
                         go = go && e < (256u << 4) && nl < room;      // a literal within the table, and room for it
                         lw |= go ? (e >> 4) << (8 * k) : 0u;
                         used += go ? e & 15u : 0u;
@@ -335,7 +345,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     if (p >= 32u) advance();
                 }
                 const uint32_t x = peek();
-                const uint32_t e = tab.get(kLitEnt0, x & ((1u << kLitBits) - 1u));
+                const uint32_t e = tab.get_lit(x & ((1u << kLitBits) - 1u));
                 const uint32_t nb = e & 15u, ls = (e >> 4) - 257u;
                 const bool is_len = ls < 29u && nb != 0u;                     // a length symbol of the table
                 const uint32_t info = s_len[is_len ? ls : 0u];
@@ -343,12 +353,12 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 const uint32_t len = (info >> 16) + ((x >> nb) & ((1u << eb) - 1u));    // <= 8 + 5 bits of 32
                 const uint32_t p2 = p + nb + eb;                                // < 32 + 13
                 const uint32_t y = peek_at(p2);
-                const uint32_t d = tab.get(kDistEnt0, y & ((1u << kDistBits) - 1u));
-                const uint32_t dnb = d & 15u, dsym = (d >> 4) & 31u;
+                const uint32_t d = tab.get_dist(y & ((1u << kDistBits) - 1u));
+                const uint32_t dnb = d & 7u, dsym = d >> 3;
                 const uint32_t de = s_dsym[dsym];
                 const uint32_t deb = de & 15u;
                 const uint32_t dist = (de >> 8) + ((y >> dnb) & ((1u << deb) - 1u));   // <= 7 + 13 bits of 32
-                const bool copy = is_len && dnb != 0u && (d >> 4) < 30u && dist <= o && len <= out_cap - o;
+                const bool copy = is_len && dnb != 0u && dsym < 30u && dist <= o && len <= out_cap - o;
                 if (copy) {
                     p = p2 + dnb + deb;                                         // < 45 + 20
                     tokp[ntok++] = pend | (len << 8) | ((dist - 1u) << 17);
@@ -359,7 +369,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 } else if (e >= (256u << 4) || o >= out_cap) {
                     // ---- `other`: not a copy the tables decode, and not a literal the next trip takes
                     uint32_t e2 = e;
-                    if ((e2 & 15u) == 0) e2 = split_slow(x, tab, kCntLEnt0, my->sorted_l, kLitBits, my->resume_l);
+                    if ((e2 & 15u) == 0) e2 = split_slow(x, beyond_l, 9, my->sorted_l, kLitBits, my->resume_l);
                     const uint32_t nb2 = e2 & 15u, sym = e2 >> 4;
                     if (nb2 == 0) {
                         fail(HDLZ_ST_BAD_CODE);                                 // no such code ("Invalid data")
@@ -379,8 +389,9 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         p += nb2 + eb2;
                         if (p >= 32u) advance();
                         const uint32_t y2 = peek();
-                        uint32_t d2 = tab.get(kDistEnt0, y2 & ((1u << kDistBits) - 1u));
-                        if ((d2 & 15u) == 0) d2 = split_slow(y2, tab, kCntDEnt0, my->sorted_d, kDistBits, my->resume_d);
+                        const uint32_t dq = tab.get_dist(y2 & ((1u << kDistBits) - 1u));
+                        uint32_t d2 = ((dq >> 3) << 4) | (dq & 7u);                  // -> (symbol << 4 | length)
+                        if ((d2 & 15u) == 0) d2 = split_slow(y2, beyond_d, 8, my->sorted_d, kDistBits, my->resume_d);
                         const uint32_t dnb2 = d2 & 15u;
                         if (dnb2 == 0 || (d2 >> 4) >= 30u) {
                             fail(HDLZ_ST_BAD_CODE);
@@ -446,19 +457,15 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     bad = (nlen > 286 || ndist > 30) ? 1u : 0u;
                     for (int i = 0; i < 19; ++i) lens[i] = 0;
                     for (uint32_t i = 0; i < ncode; ++i) lens[c_clorder[i]] = (uint8_t)get(3);
-                    // code-length code: 7-bit table in the distance table's place, its arrays in the distance code's
-                    if (!bad) bad = split_build(lens, 19, tab, kDistEnt0, 7, kCntDEnt0, my->sorted_d, my->resume_d, false);
-                    if (!bad) {
-                        uint32_t any = 0;
-                        for (int l = 1; l <= 7; ++l) any |= tab.get(kCntDEnt0, l);
-                        if (!any) bad = 1;
-                    }
+                    // code-length code: 7-bit table in the distance table's place, its arrays in the distance code's;
+                    // it must be complete and not empty (zlib: "invalid code lengths set")
+                    if (!bad) bad = split_build<false>(lens, 19, tab, 7, 8, my->sorted_d, my->resume_d, false, &beyond_d) ? 1u : 0u;
                     uint32_t idx = 0, prev = 0;
                     const uint32_t total = nlen + ndist;
                     while (!bad && idx < total) {
                         if (wi > nfull + 4) { bad = 2; break; }
-                        const uint32_t e = tab.get(kDistEnt0, peek() & 127u);
-                        const uint32_t nb = e & 15u, sym = e >> 4;
+                        const uint32_t e = tab.get_dist(peek() & 127u);
+                        const uint32_t nb = e & 7u, sym = e >> 3;
                         if (nb == 0) { bad = 1; break; }
                         p += nb;
                         if (p >= 32u) advance();
@@ -475,8 +482,9 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     }
                     if (!bad && lens[256] == 0) bad = 1;                         // no end-of-block code
                 }
-                if (!bad) bad = split_build(lens + nlen, (int)ndist, tab, kDistEnt0, kDistBits, kCntDEnt0, my->sorted_d, my->resume_d, true);
-                if (!bad) bad = split_build(lens, (int)nlen, tab, kLitEnt0, kLitBits, kCntLEnt0, my->sorted_l, my->resume_l, true);
+                // an empty distance code is legal (a block of literals only): any use of it fails later
+                if (!bad) bad = split_build<false>(lens + nlen, (int)ndist, tab, kDistBits, 8, my->sorted_d, my->resume_d, true, &beyond_d) == 1 ? 1u : 0u;
+                if (!bad) bad = split_build<true>(lens, (int)nlen, tab, kLitBits, 9, my->sorted_l, my->resume_l, true, &beyond_l) == 1 ? 1u : 0u;
                 if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
                 else state = S_BLOCK;
             }
@@ -795,7 +803,7 @@ int launch_inflate_split(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_i
     uint4 *rec = reinterpret_cast<uint4 *>(pool);
     uint32_t *tokbuf = reinterpret_cast<uint32_t *>(rec + max_items);
     uint32_t *litbuf = tokbuf + (size_t)max_items * tokcap;
-    const size_t dec_smem = (size_t)kDecWarps * (kTabEntries * 64 + 1024);
+    const size_t dec_smem = (size_t)kDecWarps * (kTabBytes + kRingBytes);
     const size_t res_smem = (size_t)kWinBytes + kBitmapBytes;
     if (!ctx->split_attr_set) {
         HDLZ_CUDA(cudaFuncSetAttribute(k_decode_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
