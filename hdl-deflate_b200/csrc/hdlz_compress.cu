@@ -329,10 +329,9 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         }
                         const uint32_t n = (uint32_t)shr64_clamp(sum, f);     // sum = n << f
                         const uint32_t x = ((k < 4 ? bv.x : bv.y) >> (8 * (k & 3))) & 255u;
-                        // a compact record, not the token: bits 24..29 = 4 * (length - 1) (what the parse needs),
-                        // bit 8 = match, low bits the mask bit of the distance or the literal byte.  The code bits
-                        // are built in P3, only for the positions where a token really starts.
-                        const uint32_t tk = m3 ? (n << 26) + ((8u << 24) | 0x100u) + f : x;
+                        const uint32_t mt = (m3 ? DC[f] : 0u) + (__brev(n + 1) >> 25) + (n << 26);
+                        const uint32_t lt = LT[x];
+                        const uint32_t tk = m3 ? mt : lt;
                         tokv[k] = tk;
                         const uint32_t ls = tk >> 24;                       // 4 * (length - 1)
                         const uint32_t look = (uint32_t)(H >> ls) & 15u;
@@ -353,6 +352,10 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 for (int grp = 1; grp >= 0; --grp) group(grp, std::false_type());
             }
             __syncwarp();
+            if (last_tile) {            // positions past the end of the stream emit nothing
+                for (int i = (int)n_tile + lane; i < kTile; i += 32) Rw[i + (i >> 5)] = 0;
+                __syncwarp();
+            }
 
             // ---------------- P2: entry skip count of every segment ----------------------------------
             uint32_t entry = 0;
@@ -373,25 +376,23 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             }
 
             // ---------------- P3: this lane's tokens -> its private bitstream --------------------------
-            // The lane walks the tokens that START in its segment (the greedy parse `di += match` / `di += 1`,
-            // deflate.py:960, 1008, from its entry skip count) and builds each one here: a literal's code from LT,
-            // a match's from DC[mask bit] plus the 7-bit length code (DISTANCE, deflate.py:836-882).
             uint32_t nbits;
             {
-                uint32_t fill = 0, wcnt = 0;
+                uint32_t r = entry, fill = 0, wcnt = 0;
                 unsigned long long acc = 0;
                 const int rbase = 33 * lane;
-                // positions of the segment that exist (the last tile ends inside one)
-                const int jend = (int)n_tile - 32 * lane < kSeg ? (int)n_tile - 32 * lane : kSeg;
-                for (int j = (int)entry; j < jend;) {
-                    const uint32_t rec = Rw[rbase + j];
-                    const bool is_match = (rec & 0x100u) != 0u;
-                    const uint32_t n = ((rec >> 24) - 8u) >> 2;                 // extension of a match (length 3 + n)
-                    const uint32_t tk = LT[is_match ? 256u + (rec & 31u) : rec & 255u] + (is_match ? __brev(n + 1) >> 25 : 0u);
-                    acc |= (unsigned long long)(tk & 0x7FFFu) << fill;
-                    fill += (tk >> 16) & 15u;
-                    j += 1 + (int)(rec >> 26);
-                    if (fill >= 32) {                        // fill < 32 + 15 between checks
+#pragma unroll 4
+                for (int j = 0; j < kSeg; j += 2) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t tk = Rw[rbase + j + u];
+                        const bool start = r == 0;
+                        const uint32_t tke = start ? tk : 0u;
+                        acc |= (unsigned long long)(tke & 0x7FFFu) << fill;
+                        fill += (tke >> 16) & 15u;
+                        r = start ? (tk >> 26) : r - 1;
+                    }
+                    if (fill >= 32) {                        // fill < 32 + 2 * 15 < 64 between checks
                         priv[wcnt * 32 + lane] = (uint32_t)acc;
                         ++wcnt;
                         acc >>= 32;
