@@ -33,7 +33,7 @@ F_PERSIST_TABLES = 16  # decompress: keep the dynamic-block decode tables in the
 CONTAINER_ZLIB, CONTAINER_RAW, CONTAINER_GZIP = 0, 1, 2
 
 STATUS_NAMES = ("OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR", "TRUNCATED",
-                "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER", "BAD_CRC")
+                "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER", "BAD_CRC", "NO_CODE")
 
 # the message the reference raises for the condition (deflate.py:721, 1140, 1508, 1539, 1560)
 REFERENCE_MESSAGES = {
@@ -46,6 +46,7 @@ REFERENCE_MESSAGES = {
     7: "Invalid data",
     8: "unexpected mode",
     9: "Invalid data",
+    11: "the tree has no code for a symbol of this stream",
 }
 
 
@@ -135,12 +136,62 @@ class Engine(object):
     def container(self, kind):
         self._check(self._lib.hdlz_set_container(self._ctx, int(kind)))
 
+    # ---- the code the compressor writes with (README.md:43-45 "dedicated pre-computed Huffman tree") ----
+    @property
+    def tree(self):
+        """None (the reference's fixed code) or (lit_len uint8[286], dist_len uint8[30])."""
+        lit, dist = np.zeros(286, np.uint8), np.zeros(30, np.uint8)
+        if not self._lib.hdlz_get_tree(self._ctx, _ptr(lit), _ptr(dist)):
+            return None
+        return lit, dist
+
+    def set_tree(self, lit_len=None, dist_len=None):
+        """Install code lengths (hdlz_set_tree); no arguments = back to the fixed code."""
+        if lit_len is None and dist_len is None:
+            self._check(self._lib.hdlz_set_tree(self._ctx, None, None))
+            return
+        lit = np.ascontiguousarray(lit_len, dtype=np.uint8)
+        dist = np.ascontiguousarray(dist_len, dtype=np.uint8)
+        if lit.shape != (286,) or dist.shape != (30,):
+            raise ValueError("lit_len needs 286 entries and dist_len 30")
+        self._check(self._lib.hdlz_set_tree(self._ctx, _ptr(lit), _ptr(dist)))
+
+    def train_tree(self, blocks, lens=None):
+        """Count the symbols of the parse of `blocks` (uint8 [n, in_stride], host) on the GPU and install the
+        optimal length-limited code for them (hdlz_train_tree).  -> the installed (lit_len, dist_len)."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+        n, in_stride = blocks.shape
+        if in_stride % 16:
+            raise ValueError("in_stride must be a multiple of 16")
+        d_in, d_len = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self._lib.hdlz_dev_alloc(self._ctx, blocks.nbytes, ctypes.byref(d_in)))
+        try:
+            self._check(self._lib.hdlz_copy_h2d(self._ctx, d_in, _ptr(blocks), blocks.nbytes, None))
+            if lens is not None:
+                lens = np.ascontiguousarray(lens, dtype=np.uint32)
+                self._check(self._lib.hdlz_dev_alloc(self._ctx, lens.nbytes, ctypes.byref(d_len)))
+                self._check(self._lib.hdlz_copy_h2d(self._ctx, d_len, _ptr(lens), lens.nbytes, None))
+            self.train_tree_device(d_in.value, in_stride, d_len.value, in_stride, n)
+        finally:
+            self._lib.hdlz_dev_free(self._ctx, d_in)
+            if d_len.value:
+                self._lib.hdlz_dev_free(self._ctx, d_len)
+        return self.tree
+
+    def train_tree_device(self, d_in, in_stride, d_in_len, uniform_len, n, stream=0):
+        self._check(self._lib.hdlz_train_tree(self._ctx, _ptr(d_in), in_stride, _ptr(d_in_len), uniform_len, n,
+                                              stream or None))
+
+    def bound(self, n):
+        """Slot size a stream of n input bytes needs with the current container and code."""
+        return int(self._lib.hdlz_compress_bound_tree(self._ctx, int(n)))
+
     # ---- one stream: a STARTC / STARTD job ---------------------------------------------
     def compress(self, data):
         """zlib stream of `data`, bit-identical to the reference's FAST+MATCH10 output."""
         data = bytes(data)
         src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
-        cap = compress_bound(len(data), self.container)
+        cap = self.bound(len(data))
         out = np.empty(cap, dtype=np.uint8)
         n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
         self._check(self._lib.hdlz_compress_stream(self._ctx, src.ctypes.data, len(data), out.ctypes.data, cap,
@@ -178,7 +229,7 @@ class Engine(object):
         else:
             maxlen = in_stride
         if out_stride is None:
-            out_stride = compress_bound(maxlen, self.container)
+            out_stride = self.bound(maxlen)
         out = np.empty((n, out_stride), dtype=np.uint8)
         out_len = np.zeros(n, dtype=np.uint32)
         status = np.zeros(n, dtype=np.uint32)
@@ -196,7 +247,7 @@ class Engine(object):
             maxlen = int(lens.max()) if n else 0
         else:
             maxlen = in_stride
-        cap = n * compress_bound(maxlen, self.container)
+        cap = n * self.bound(maxlen)
         out = np.empty(max(cap, 16), dtype=np.uint8)
         off = np.zeros(n, dtype=np.uint64)
         out_len = np.zeros(n, dtype=np.uint32)

@@ -27,6 +27,12 @@ SIGNATURES = {
     "hdlz_set_container": (cint, [vp, cint]),
     "hdlz_get_container": (cint, [vp]),
     "hdlz_compress_bound_ex": (u32, [u32, cint]),
+    "hdlz_set_tree": (cint, [vp, c_u8p, c_u8p]),
+    "hdlz_get_tree": (cint, [vp, c_u8p, c_u8p]),
+    "hdlz_train_tree": (cint, [vp, c_u8p, u64, c_u32p, u32, u64, vp]),
+    "hdlz_compress_bound_tree": (u32, [vp, u32]),
+    "hdlz_tree_lengths": (cint, [c_u64p, cint, cint, c_u8p]),
+    "hdlz_tree_header": (cint, [c_u8p, c_u8p, cint, c_u8p, u32, ctypes.POINTER(u32)]),
     "hdlz_compress_batch": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u32p, c_u32p, u64, vp]),
     "hdlz_decompress_batch": (cint, [vp, c_u8p, c_u64p, u64, c_u32p, c_u8p, u64, u32, c_u32p, c_u32p, u64, u32, vp]),
     "hdlz_compress_host": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u32p, c_u32p, u64]),

@@ -127,7 +127,7 @@ const char *hdlz_status_name(uint32_t s)
 {
     static const char *names[] = {"OK", "SHORT_INPUT", "BAD_BTYPE", "BAD_CODE", "DIST_TOO_FAR",
                                   "TRUNCATED", "OUT_OVERFLOW", "BAD_STORED", "BAD_HEADER", "BAD_ADLER",
-                                  "BAD_CRC"};
+                                  "BAD_CRC", "NO_CODE"};
     return s < sizeof(names) / sizeof(names[0]) ? names[s] : "UNKNOWN";
 }
 
@@ -196,6 +196,7 @@ int hdlz_destroy(hdlz_ctx *c)
     }
     if (c->h_dyn_seen) cudaFreeHost(c->h_dyn_seen);
     if (c->d_queue) cudaFree(c->d_queue);
+    if (c->d_tree) cudaFree(c->d_tree);
     if (c->d_pack) cudaFree(c->d_pack);
     for (int i = 0; i < 3; i++)
         if (c->d_lane[i]) cudaFree(c->d_lane[i]);
@@ -397,7 +398,8 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
         maxlen = 0;
         for (uint64_t i = 0; i < n; i++) maxlen = in_len[i] > maxlen ? in_len[i] : maxlen;
     }
-    const uint64_t slot = compress_bound(maxlen, ctx->container);
+    if ((rc = refresh_tree(ctx))) return rc;
+    const uint64_t slot = ctx->tree_set ? tree_bound(ctx, maxlen) : compress_bound(maxlen, ctx->container);
     const uint64_t chunk = host_chunk(n, in_stride + slot);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, (size_t)n * in_stride))) return rc;
@@ -470,7 +472,8 @@ int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t
     if (len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
     *out_len = 0;
     const size_t in_slot = ((size_t)len + 15) & ~(size_t)15;
-    const size_t out_slot = compress_bound(len, ctx->container);
+    if ((rc = refresh_tree(ctx))) return rc;
+    const size_t out_slot = ctx->tree_set ? tree_bound(ctx, len) : compress_bound(len, ctx->container);
     if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, in_slot + 16))) return rc;
     if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, out_slot))) return rc;
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * sizeof(uint32_t)))) return rc;
@@ -594,6 +597,7 @@ int hdlz_cstream_begin(hdlz_ctx *ctx, hdlz_cstream **out)
     *out = nullptr;
     if (ctx->container == HDLZ_CONTAINER_GZIP)
         return set_error(HDLZ_ERR_INVALID, "streams fed in pieces write the zlib or the raw container (the gzip CRC-32 is taken over the whole input)");
+    if (ctx->tree_set) return set_error(HDLZ_ERR_INVALID, "streams fed in pieces code with the fixed tree (hdlz_set_tree is for whole-stream and batch calls)");
     if (ctx->window != HDLZ_CWINDOW) return set_error(HDLZ_ERR_INVALID, "streams fed in pieces use the FAST engine (CWINDOW = 32)");
     hdlz_cstream *st = new hdlz_cstream();
     memset(st, 0, sizeof *st);

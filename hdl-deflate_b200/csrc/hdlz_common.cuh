@@ -14,6 +14,25 @@
 #define HDLZ_F_NO_LANE_SCRATCH 0x400u /* lanes hand dynamic-block streams to the warp-per-stream kernel */
 #define HDLZ_F_NO_SPLIT 0x1000u       /* dynamic-block streams stay on the lane-per-stream kernel (no two-phase route) */
 
+namespace hdlz {
+// The code a compressor context uses instead of the fixed one (hdlz_tree.cu): token tables of the kernels and the
+// bit string every stream starts with (container header, BFINAL / BTYPE = 10, the code description).
+constexpr int kTreeLenBase = 288;       // lut[288 + n]: length symbol of a match of 3 + n bytes
+constexpr int kTreeLutWords = 296;
+constexpr int kTreePrefixWords = 80;    // 80 header bits (gzip) + 17 + 19 * 3 + 316 * 7 bits at most
+constexpr int kTreeHistWords = 296;     // hdlz_train_tree: counts in the layout of lut
+struct TreeDev {
+    uint32_t lut[kTreeLutWords];        // [0..255] literal: code | bits << 16;  [256 + f] distance 32 - f: code and extra
+                                        // bits | bits << 24;  [288 + n]: code | bits << 16
+    uint32_t dist[256];                 // distance d at [d - 1], as lut[256 + f] (the CWINDOW = 256 kernel)
+    uint32_t eob;                       // code | bits << 16
+    uint32_t prefix_bits;
+    uint32_t worst_bits;                // most bits one input byte can cost
+    uint32_t pad;
+    uint32_t prefix[kTreePrefixWords];
+};
+}  // namespace hdlz
+
 struct hdlz_ctx {
     int device;
     int sm_count;
@@ -22,6 +41,13 @@ struct hdlz_ctx {
     uint32_t window;     // search window of the compressor: 32 (FAST, default) or 256 (FAST = False, deflate.py:56-59)
     bool wide_attr_set;
     bool stream_attr_set;
+    bool tree_attr_set;
+    // application / trained code (hdlz_set_tree, hdlz_train_tree); tree_set false = the reference's fixed code
+    bool tree_set;
+    uint32_t tree_container;   // container the prefix of `tree` was built for
+    uint8_t tree_lit[286], tree_dist[30];
+    hdlz::TreeDev tree;        // host image of *d_tree
+    hdlz::TreeDev *d_tree;
     // scratch for the host-buffer entry points (grown on demand, reused)
     uint8_t *d_in;
     size_t d_in_cap;
@@ -111,6 +137,10 @@ int cuda_fail(cudaError_t e, const char *what);
 int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                     uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
                     uint32_t *d_status, uint64_t n, cudaStream_t s);
+int launch_compress_hist(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len, uint32_t uniform_len,
+                         uint64_t n, unsigned long long *d_hist, cudaStream_t s);
+int refresh_tree(hdlz_ctx *ctx);
+uint32_t tree_bound(const hdlz_ctx *ctx, uint32_t len);
 int launch_compress_wide(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                          uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
                          uint32_t *d_status, uint64_t n, unsigned long long *queue, cudaStream_t s);

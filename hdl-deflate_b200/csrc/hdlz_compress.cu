@@ -55,23 +55,28 @@ constexpr int kCtasPerSm = 8;
 constexpr int kInBytes = 32 + kTile + 32;              // history | tile | look-ahead chunk
 // a lane's private stream holds the tokens that START in its segment: at most 31 nine-bit literals
 // plus one 15-bit match token at the last position = 294 bits
-constexpr int kPrivWords = ((kSeg - 1) * 9 + 15 + 31) / 32;   // 10
-constexpr int kStageBytes = kPrivWords * 32 * 4;       // 1280 >= kInBytes: input tile, later the private streams
+// With an application / trained code (kMode 1, hdlz_tree.cu) a literal costs up to 15 bits and a match up to
+// 15 + 15 + 3: the private streams and the tile's stream are sized for that.
+constexpr int kModeFixed = 0, kModeTree = 1, kModeHist = 2;
+__host__ __device__ constexpr int priv_words(int mode) { return mode == kModeTree ? ((kSeg - 1) * 15 + 33 + 31) / 32 : ((kSeg - 1) * 9 + 15 + 31) / 32; }   // 16 : 10
+__host__ __device__ constexpr int out_words(int mode) { return mode == kModeTree ? 488 : 296; }   // 31 carry bits + 1024 * (15 : 9) + EOB + trailer, rounded up
 constexpr int kRWords = (kTile + 32) + (kTile + 32) / kSeg;   // padded: idx = i + i/32  (1089 incl. last +1)
-constexpr int kOutWords = 296;                         // 31 carry bits + 1024*9 + EOB + Adler, rounded up
 
-static_assert(kStageBytes >= kInBytes, "stage buffer must hold the input tile");
-
-struct __align__(16) WarpSmem {
+template <int kMode>
+struct __align__(16) WarpSmemT {
+    static constexpr int kStageBytes = priv_words(kMode) * 32 * 4;   // 1280 (2048) >= kInBytes: input tile, later the private streams
     uint8_t stage[kStageBytes];                        // input tile, then the segment maps, then the lane-private streams
     uint32_t R[(kRWords + 4) / 4 * 4];                 // masks, overwritten in place by tokens; after P3 the
-                                                       // tile's part of the output stream (kOutWords words)
+                                                       // tile's part of the output stream (out_words words)
     uint32_t T[256];                                   // value -> lane mask of the previous chunk
+    static_assert(kStageBytes >= kInBytes, "stage buffer must hold the input tile");
+    static_assert(out_words(kMode) <= kRWords, "the output stream part must fit in the token array");
 };
-static_assert(kOutWords <= kRWords, "the output stream part must fit in the token array");
 
-constexpr int kLutWords = 256 + 36;   // LT[256] literal tokens, DC[33] distance part of match tokens
-constexpr size_t kSmemBytes = kLutWords * 4 + sizeof(WarpSmem) * kWarpsPerCta;
+constexpr int kLutWords = kTreeLutWords;   // LT[256] literal tokens, DC[32 + 4] distance part of match tokens (by mask bit), 8 length symbols (tree)
+static_assert(kLutWords >= 256 + 36, "fixed-code tables");
+template <int kMode>
+constexpr size_t smem_bytes() { return kLutWords * 4 + sizeof(WarpSmemT<kMode>) * kWarpsPerCta; }
 
 // token word: bits 0..14 code (LSB-first), 16..19 bit count, 24..29 = 4 * (length in positions - 1),
 // i.e. the nibble shift of the parse DP
@@ -142,22 +147,33 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 // position (`di`), both Adler sums — and writes the words it completes to out[0 ..]; `in` is the address the
 // stream's byte 0 would have (only bytes from t0 - 32 on are read).  The last launch (ctl->final) knows the true
 // length and closes the stream.  Compiled out of the batch kernel.
-template <int kMaxMatch, bool kStream>
+// kMode: kModeFixed = the reference's fixed code; kModeTree = the code of *tree (hdlz_set_tree / hdlz_train_tree): same
+// parse, every stream starts with tree->prefix, tokens come from tree->lut; kModeHist = no output, the symbols the
+// parse produces are counted into hist[] (hdlz_train_tree).
+template <int kMaxMatch, bool kStream, int kMode>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len,
            uint32_t uniform_len, uint8_t *__restrict__ out, uint64_t out_stride,
            uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue,
-           uint32_t container, StreamCtl *ctl)
+           uint32_t container, StreamCtl *ctl, const TreeDev *__restrict__ tree, unsigned long long *hist)
 {
     extern __shared__ uint4 smem_raw[];
     uint32_t *LT = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *DC = LT + 256;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    using WarpSmem = WarpSmemT<kMode>;
+    constexpr int kOutWords = out_words(kMode);
     WarpSmem &ws = reinterpret_cast<WarpSmem *>(LT + kLutWords)[warp];
 
-    for (int i = threadIdx.x; i < 256; i += kWarpsPerCta * 32) LT[i] = literal_token_entry((uint32_t)i);
-    if (threadIdx.x < 36) DC[threadIdx.x] = threadIdx.x < 32 ? dist_token_entry(31 - (int)threadIdx.x) : 0u;   // by mask bit: d = 32 - f
+    if constexpr (kMode == kModeFixed) {
+        for (int i = threadIdx.x; i < 256; i += kWarpsPerCta * 32) LT[i] = literal_token_entry((uint32_t)i);
+        if (threadIdx.x < 36) DC[threadIdx.x] = threadIdx.x < 32 ? dist_token_entry(31 - (int)threadIdx.x) : 0u;   // by mask bit: d = 32 - f
+    } else if constexpr (kMode == kModeTree) {
+        for (int i = threadIdx.x; i < kTreeLutWords; i += kWarpsPerCta * 32) LT[i] = tree->lut[i];
+    } else {
+        for (int i = threadIdx.x; i < kTreeHistWords; i += kWarpsPerCta * 32) LT[i] = 0;      // the CTA's counts
+    }
     __syncthreads();
 
     uint8_t *in_s = ws.stage;                                  // byte i <-> position t0 - 32 + i
@@ -180,8 +196,13 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         const uint32_t L = in_len ? in_len[sid] : uniform_len;
         const uint8_t *src = in + sid * in_stride;
         uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + sid * out_stride);
-        if (!kStream && (L < HDLZ_MIN_INPUT || (uint64_t)compress_bound(L, container) > out_stride)) {
-            if (lane == 0) {
+        uint64_t need = 0;               // slot size this stream may need
+        if constexpr (kMode == kModeFixed) need = compress_bound(L, container);
+        else if constexpr (kMode == kModeTree)
+            need = ((((uint64_t)tree->prefix_bits + (uint64_t)L * tree->worst_bits + (tree->eob >> 16) + 7) >> 3) +
+                    (container == HDLZ_CONTAINER_GZIP ? 8u : container == HDLZ_CONTAINER_RAW ? 0u : 4u) + 15) & ~15ull;
+        if (!kStream && (L < HDLZ_MIN_INPUT || need > out_stride)) {
+            if (lane == 0 && kMode != kModeHist) {
                 out_len[sid] = 0;
                 if (status) status[sid] = L < HDLZ_MIN_INPUT ? HDLZ_ST_SHORT_INPUT : HDLZ_ST_OUT_OVERFLOW;
             }
@@ -195,7 +216,17 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         uint32_t pw = 0x78u | (0x9Cu << 8) | (3u << 16);
         uint32_t lbit = 19;              // valid bits in pw
         uint32_t wbase = 0;              // 32-bit words of the stream already written to HBM
-        if (container == HDLZ_CONTAINER_RAW) {
+        uint32_t uncoded = 0;            // kModeTree: a token whose symbol has no code in the tree
+        if constexpr (kMode == kModeTree) {
+            // container header, BFINAL = 1 / BTYPE = 10 and the code description: the same bits in every stream
+            const uint32_t nfp = tree->prefix_bits >> 5;
+            for (uint32_t k = lane; k < nfp; k += 32) dst32[k] = tree->prefix[k];
+            pw = tree->prefix[nfp];
+            lbit = tree->prefix_bits & 31u;
+            wbase = nfp;
+        } else if constexpr (kMode == kModeHist) {
+            // nothing is written
+        } else if (container == HDLZ_CONTAINER_RAW) {
             pw = 3u;
             lbit = 3;
         } else if (container == HDLZ_CONTAINER_GZIP) {
@@ -329,9 +360,17 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                         }
                         const uint32_t n = (uint32_t)shr64_clamp(sum, f);     // sum = n << f
                         const uint32_t x = ((k < 4 ? bv.x : bv.y) >> (8 * (k & 3))) & 255u;
-                        const uint32_t mt = (m3 ? DC[f] : 0u) + (__brev(n + 1) >> 25) + (n << 26);
-                        const uint32_t lt = LT[x];
-                        const uint32_t tk = m3 ? mt : lt;
+                        uint32_t tk;
+                        if constexpr (kMode == kModeFixed) {
+                            const uint32_t mt = (m3 ? DC[f] : 0u) + (__brev(n + 1) >> 25) + (n << 26);
+                            const uint32_t lt = LT[x];
+                            tk = m3 ? mt : lt;
+                        } else {
+                            // a compact record, not the token: bits 24..29 = 4 * (length - 1) (what the parse needs),
+                            // bit 8 = match, low bits the mask bit of the distance or the literal byte; P3 looks the
+                            // codes up (or counts the symbols)
+                            tk = m3 ? (n << 26) + ((8u << 24) | 0x100u) + f : x;
+                        }
                         tokv[k] = tk;
                         const uint32_t ls = tk >> 24;                       // 4 * (length - 1)
                         const uint32_t look = (uint32_t)(H >> ls) & 15u;
@@ -352,7 +391,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 for (int grp = 1; grp >= 0; --grp) group(grp, std::false_type());
             }
             __syncwarp();
-            if (last_tile) {            // positions past the end of the stream emit nothing
+            if (kMode == kModeFixed && last_tile) {            // positions past the end of the stream emit nothing
                 for (int i = (int)n_tile + lane; i < kTile; i += 32) Rw[i + (i >> 5)] = 0;
                 __syncwarp();
             }
@@ -377,7 +416,53 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 
             // ---------------- P3: this lane's tokens -> its private bitstream --------------------------
             uint32_t nbits;
-            {
+            if constexpr (kMode != kModeFixed) {
+                // records -> codes of the tree (a match is two puts: length symbol, then distance code + extra bits;
+                // DISTANCE, deflate.py:836-882), or -> counts
+                uint32_t r = entry, fill = 0, wcnt = 0;
+                unsigned long long acc = 0;
+                const int rbase = 33 * lane;
+                const int jend = (int)n_tile - 32 * lane;       // positions of the segment that exist (the last tile ends inside one)
+#pragma unroll 4
+                for (int j = 0; j < kSeg; ++j) {
+                    const uint32_t rec = Rw[rbase + j];
+                    const bool start = r == 0 && j < jend;
+                    const bool is_match = (rec & 0x100u) != 0u;
+                    const uint32_t n = ((rec >> 24) - 8u) >> 2;                 // extension of a match (length 3 + n)
+                    const uint32_t i1 = is_match ? (uint32_t)kTreeLenBase + n : rec & 255u;
+                    const uint32_t i2 = 256u + (rec & 31u);
+                    if constexpr (kMode == kModeHist) {
+                        if (start) {
+                            atomicAdd(&LT[i1], 1u);
+                            if (is_match) atomicAdd(&LT[i2], 1u);
+                        }
+                    } else {
+                        uint32_t e1 = LT[i1];
+                        uint32_t e2 = is_match ? LT[i2] : 0u;
+                        if (start && ((e1 >> 16) == 0u || (is_match && (e2 >> 24) == 0u))) uncoded = 1;
+                        if (!start) { e1 = 0; e2 = 0; }
+                        acc |= (unsigned long long)(e1 & 0xFFFFu) << fill;
+                        fill += e1 >> 16;
+                        if (fill >= 32) {
+                            priv[wcnt * 32 + lane] = (uint32_t)acc;
+                            ++wcnt;
+                            acc >>= 32;
+                            fill -= 32;
+                        }
+                        acc |= (unsigned long long)(e2 & 0xFFFFFFu) << fill;
+                        fill += e2 >> 24;
+                        if (fill >= 32) {
+                            priv[wcnt * 32 + lane] = (uint32_t)acc;
+                            ++wcnt;
+                            acc >>= 32;
+                            fill -= 32;
+                        }
+                    }
+                    r = r == 0 ? rec >> 26 : r - 1;
+                }
+                if (fill) priv[wcnt * 32 + lane] = (uint32_t)acc;
+                nbits = 32 * wcnt + fill;
+            } else {
                 uint32_t r = entry, fill = 0, wcnt = 0;
                 unsigned long long acc = 0;
                 const int rbase = 33 * lane;
@@ -402,6 +487,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 if (fill) priv[wcnt * 32 + lane] = (uint32_t)acc;     // wcnt <= kPrivWords - 1 here
                 nbits = 32 * wcnt + fill;
             }
+            if constexpr (kMode == kModeHist) continue;       // counted: nothing is written
             uint32_t incl = nbits;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -447,7 +533,18 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 wbase += nfull;
                 lbit = total & 31;
             } else {
-                total += 7;                                   // EOB: seven zero bits (deflate.py:772-779)
+                if constexpr (kMode == kModeTree) {           // EOB with the tree's code for symbol 256
+                    const uint32_t eob = tree->eob;
+                    if (lane == 0) {
+                        const unsigned long long v = (unsigned long long)(eob & 0xFFFFu) << (total & 31u);
+                        outw[total >> 5] |= (uint32_t)v;
+                        outw[(total >> 5) + 1] |= (uint32_t)(v >> 32);
+                    }
+                    __syncwarp();
+                    total += eob >> 16;
+                } else {
+                    total += 7;                               // EOB: seven zero bits (deflate.py:772-779)
+                }
                 const uint32_t nbytes = (total + 7) >> 3;     // pad to a byte (deflate.py:784-787)
                 uint32_t trailer = 4;
                 if (lane == 0) {
@@ -470,9 +567,10 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 __syncwarp();
                 const uint32_t nwords = (nbytes + trailer + 3) >> 2;
                 for (uint32_t k = lane; k < nwords; k += 32) dst32[wbase + k] = outw[k];
+                const bool no_code = kMode == kModeTree && __any_sync(HDLZ_FULL_MASK, uncoded != 0u);
                 if (lane == 0) {
-                    out_len[sid] = 4 * wbase + nbytes + trailer;
-                    if (status) status[sid] = HDLZ_OK;
+                    out_len[sid] = no_code ? 0u : 4 * wbase + nbytes + trailer;
+                    if (status) status[sid] = no_code ? HDLZ_ST_NO_CODE : HDLZ_OK;
                 }
             }
         }
@@ -492,6 +590,11 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         }
         sid = n_warps + __shfl_sync(HDLZ_FULL_MASK, next_ticket, 0);
     }
+    if constexpr (kMode == kModeHist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kTreeHistWords; i += kWarpsPerCta * 32)
+            if (LT[i]) atomicAdd(&hist[i], (unsigned long long)LT[i]);
+    }
 }
 
 }  // namespace
@@ -501,19 +604,75 @@ int launch_compress_stream(hdlz_ctx *ctx, const uint8_t *d_in_virtual, uint32_t 
                            uint32_t *d_status, StreamCtl *d_ctl, unsigned long long *d_queue, cudaStream_t s)
 {
     if (!ctx->stream_attr_set) {
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, true, kModeFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, true, kModeFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
         ctx->stream_attr_set = true;
     }
     if (ctx->max_match == 5)
-        k_compress<5, true><<<1, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status,
-                                                                      1, d_queue, ctx->container, d_ctl);
+        k_compress<5, true, kModeFixed><<<1, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
+            d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status, 1, d_queue, ctx->container, d_ctl, nullptr, nullptr);
     else
-        k_compress<10, true><<<1, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status,
-                                                                       1, d_queue, ctx->container, d_ctl);
+        k_compress<10, true, kModeFixed><<<1, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
+            d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status, 1, d_queue, ctx->container, d_ctl, nullptr, nullptr);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;
+}
+
+// queue head of one launch of the persistent grid: the next of kQueueSlots slots, zeroed on the launch's own
+// stream.  A slot comes round again after kQueueSlots compress launches of this context, far more than can be
+// in flight on its streams at once.
+static int next_queue(hdlz_ctx *ctx, unsigned long long **queue, cudaStream_t s)
+{
+    constexpr unsigned kQueueSlots = 4096;
+    if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, kQueueSlots * sizeof(unsigned long long)));
+    *queue = ctx->d_queue + (ctx->queue_seq++ & (kQueueSlots - 1));
+    HDLZ_CUDA(cudaMemsetAsync(*queue, 0, sizeof(unsigned long long), s));
+    return HDLZ_SUCCESS;
+}
+
+template <int kMode>
+static int launch_mode(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len, uint32_t uniform_len,
+                       uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len, uint32_t *d_status, uint64_t n,
+                       unsigned long long *d_hist, cudaStream_t s)
+{
+    bool &attr = kMode == kModeFixed ? ctx->compress_attr_set : ctx->tree_attr_set;
+    if (!attr) {
+        constexpr int kA = kMode == kModeFixed ? kModeFixed : kModeTree, kB = kMode == kModeFixed ? kModeFixed : kModeHist;
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kA>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kA>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kB>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kB>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
+    uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;      // persistent: a multiple of the SM count
+    if (blocks > resident) blocks = resident;
+    unsigned long long *queue = nullptr;
+    int rc = next_queue(ctx, &queue, s);
+    if (rc) return rc;
+    if (ctx->max_match == 5)
+        k_compress<5, false, kMode><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kMode>(), s>>>(
+            d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr,
+            ctx->d_tree, d_hist);
+    else
+        k_compress<10, false, kMode><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kMode>(), s>>>(
+            d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr,
+            ctx->d_tree, d_hist);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
+
+// hdlz_train_tree: the symbols of the reference's parse over the batch, counted into d_hist[kTreeHistWords]
+int launch_compress_hist(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len, uint32_t uniform_len,
+                         uint64_t n, unsigned long long *d_hist, cudaStream_t s)
+{
+    return launch_mode<kModeHist>(ctx, d_in, in_stride, d_in_len, uniform_len, nullptr, 0, nullptr, nullptr, n, d_hist, s);
 }
 
 int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
@@ -521,42 +680,20 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
                     uint32_t *d_status, uint64_t n, cudaStream_t s)
 {
     if (n == 0) return HDLZ_SUCCESS;
-    if (!ctx->compress_attr_set) {
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        ctx->compress_attr_set = true;
-    }
-    uint64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;      // persistent: a multiple of the SM count
-    if (blocks > resident) blocks = resident;
-    // queue head of this launch: the next of kQueueSlots slots, zeroed on the launch's own stream.  A slot
-    // comes round again after kQueueSlots compress launches of this context, far more than can be in
-    // flight on its streams at once.
-    constexpr unsigned kQueueSlots = 4096;
-    if (!ctx->d_queue) HDLZ_CUDA(cudaMalloc((void **)&ctx->d_queue, kQueueSlots * sizeof(unsigned long long)));
-    unsigned long long *queue = ctx->d_queue + (ctx->queue_seq++ & (kQueueSlots - 1));
-    HDLZ_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s));
+    int rc;
     if (ctx->window == 256) {
         // the reference's non-FAST configuration (CWINDOW = 256): hdlz_compress_wide.cu
-        const int rc = launch_compress_wide(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status,
-                                            n, queue, s);
-        if (rc) return rc;
-        if (ctx->container == HDLZ_CONTAINER_GZIP)
-            return launch_gzip_trailers(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, n, s);
-        return HDLZ_SUCCESS;
+        if (ctx->tree_set) return set_error(HDLZ_ERR_INVALID, "a tree (hdlz_set_tree) needs the FAST compressor (CWINDOW = 32)");
+        unsigned long long *queue = nullptr;
+        if ((rc = next_queue(ctx, &queue, s))) return rc;
+        rc = launch_compress_wide(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n, queue, s);
+    } else if (ctx->tree_set) {
+        if ((rc = refresh_tree(ctx))) return rc;
+        rc = launch_mode<kModeTree>(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n, nullptr, s);
+    } else {
+        rc = launch_mode<kModeFixed>(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n, nullptr, s);
     }
-    if (ctx->max_match == 5)
-        k_compress<5, false><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
-                                                                               d_out, out_stride, d_out_len, d_status, n, queue,
-                                                                               ctx->container, nullptr);
-    else
-        k_compress<10, false><<<(unsigned)blocks, kWarpsPerCta * 32, kSmemBytes, s>>>(d_in, in_stride, d_in_len, uniform_len,
-                                                                                d_out, out_stride, d_out_len, d_status, n, queue,
-                                                                                ctx->container, nullptr);
-    ctx->launches++;
-    HDLZ_CUDA(cudaGetLastError());
+    if (rc) return rc;
     if (ctx->container == HDLZ_CONTAINER_GZIP)
         return launch_gzip_trailers(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, n, s);
     return HDLZ_SUCCESS;

@@ -67,7 +67,8 @@ typedef enum hdlz_status {
     HDLZ_ST_BAD_STORED = 7,   /* stored block LEN != ~NLEN (reference does not check; zlib does)            */
     HDLZ_ST_BAD_HEADER = 8,   /* zlib CMF/FLG invalid — only with HDLZ_F_VERIFY_HEADER (reference skips it, deflate.py:644,665-676) */
     HDLZ_ST_BAD_ADLER = 9,    /* Adler-32 mismatch — only with HDLZ_F_VERIFY_ADLER (reference never checks, deflate.py:1535)       */
-    HDLZ_ST_BAD_CRC = 10      /* gzip CRC-32 / ISIZE mismatch — only with HDLZ_F_GZIP | HDLZ_F_VERIFY_ADLER                        */
+    HDLZ_ST_BAD_CRC = 10,     /* gzip CRC-32 / ISIZE mismatch — only with HDLZ_F_GZIP | HDLZ_F_VERIFY_ADLER                        */
+    HDLZ_ST_NO_CODE = 11      /* compress with hdlz_set_tree: the stream holds a symbol the tree has no code for                   */
 } hdlz_status;
 
 /* decompress flags */
@@ -125,6 +126,35 @@ int hdlz_get_fast(hdlz_ctx *ctx);
 int hdlz_set_container(hdlz_ctx *ctx, int container);
 int hdlz_get_container(hdlz_ctx *ctx);
 uint32_t hdlz_compress_bound_ex(uint32_t len, int container);
+
+/* The code the compressor writes with.  The reference always codes with the fixed tree of RFC 1951
+ * (out_codes, deflate.py:112-149; STATIC :1064-1076) and names "a dedicated pre-computed Huffman tree"
+ * for data with few byte values as the next step (README.md:43-45).  hdlz_set_tree installs one:
+ * code lengths (0 = unused, <= 15) of the 286 literal/length and 30 distance symbols; every later
+ * compress call of the context writes ONE dynamic-Huffman block (BTYPE = 10) per stream that opens
+ * with the description of this code and holds the same tokens deflate.py's parse produces (SEARCH /
+ * SEARCHF / DISTANCE, deflate.py:836-1016), coded with it.  Symbol 256 needs a code; a stream that
+ * needs a symbol without one ends with HDLZ_ST_NO_CODE.  Lengths must not be over-subscribed and may be
+ * incomplete only as a single one-bit code (what inflaters accept).  NULL, NULL returns to the fixed code.
+ * hdlz_train_tree builds the lengths from a batch on the device: the compress kernel counts the symbols
+ * of its parse (no output), the counts (+1 for every symbol the parse can produce, so that a later batch
+ * cannot meet a missing code) become optimal length-limited code lengths, which are installed.
+ * hdlz_get_tree returns 1 and copies the lengths when a tree is installed, 0 otherwise.
+ * hdlz_compress_bound_tree: slot size a stream of `len` bytes needs with the installed code.
+ * FAST compressor (CWINDOW = 32) only; whole-stream and batch calls (not hdlz_cstream_*).  Setting or
+ * training a tree waits for the device to go idle first (earlier launches may still read the old tables). */
+int hdlz_set_tree(hdlz_ctx *ctx, const uint8_t *lit_len /* [286] */, const uint8_t *dist_len /* [30] */);
+int hdlz_get_tree(hdlz_ctx *ctx, uint8_t *lit_len, uint8_t *dist_len);
+int hdlz_train_tree(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
+                    uint32_t uniform_len, uint64_t n, void *stream);
+uint32_t hdlz_compress_bound_tree(hdlz_ctx *ctx, uint32_t len);
+/* Device-independent helpers for an application that gathers its own statistics: optimal code lengths
+ * (<= max_bits) for `n` symbol counts (0 = unused symbol, gets length 0), and the bytes every stream of a
+ * context with these lengths starts with (container header, BFINAL / BTYPE = 10, RFC 1951 3.2.7 code
+ * description; *out_bits of them, the last byte zero-padded). */
+int hdlz_tree_lengths(const uint64_t *count, int n, int max_bits, uint8_t *len);
+int hdlz_tree_header(const uint8_t *lit_len, const uint8_t *dist_len, int container, uint8_t *out, uint32_t out_cap,
+                     uint32_t *out_bits);
 
 /* ---- compress: STARTC job (deflate.py:618-633; CSTATIC/SEARCH/SEARCHF/DISTANCE/CHECKSUM :734-1016) ----
  * Block i = d_in[i*in_stride .. +len_i), len_i = d_in_len ? d_in_len[i] : uniform_len

@@ -260,6 +260,22 @@ uint32_t hdlz_oracle_parse(const uint8_t *x, uint32_t L, uint32_t *tok, uint32_t
     return n;
 }
 
+/* The same greedy parse (SEARCH / SEARCHF, deflate.py:899-1016) as (length, distance) pairs, for streams of any
+ * length and either MATCH10 setting: tok[2i] = length (1 = literal), tok[2i+1] = distance.  Used by the tree-mode
+ * restatement (oracle/tree_oracle.py). */
+uint32_t hdlz_oracle_parse_ex(const uint8_t *x, uint32_t L, uint32_t *tok, uint32_t cap, unsigned cwindow, unsigned maxlen)
+{
+    uint32_t n = 0, p = 0;
+    while (p < L) {
+        unsigned d = 0, m = 1;
+        if (!find_match(x, L, p, cwindow, maxlen, &d, &m)) { d = 0; m = 1; }
+        if (n < cap) { tok[2 * n] = m; tok[2 * n + 1] = d; }
+        n++;
+        p += m;
+    }
+    return n;
+}
+
 /* ------------------------------------------------------------------------ */
 /* inflate restatement (zlib-wrapped RFC 1951; HEADER..COPY, :656-732,       */
 /* :1084-1659).  Parity target is zlib (test_deflate.py:194).                */
