@@ -323,6 +323,55 @@ def run_config3(eng, hz, d_plain, n, dev, stream, steps, threads, peak):
             "fixture_seconds": t_fix}
 
 
+def run_tree(eng, hz, d_plain, n, dev, stream, steps):
+    """SURVEY 8(f) rank 4 (README.md:43-45): the same blocks, and the same blocks folded onto 16 byte values
+    ("data sets with just a small set of used byte values"), compressed with a code trained on the batch
+    (hdlz_train_tree: the kernel counts the symbols of its parse, the host turns the counts into code lengths)
+    against the reference's fixed code.  Every stream is inflated again by the engine (Adler-32 verified)
+    and compared with the blocks before anything is timed."""
+    import torch
+    out = {}
+    few = (d_plain & 15) + 97
+    for name, d_src in (("config2_blocks", d_plain), ("sixteen_byte_values", few)):
+        eng.set_tree()
+        ostride = eng.bound(BLOCK)
+        d_comp = torch.empty(n * ostride, dtype=torch.uint8, device=dev)
+        d_clen = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+        eng.compress_batch(d_src, BLOCK, None, BLOCK, d_comp, ostride, d_clen, d_st, n, stream=stream)
+        torch.cuda.synchronize()
+        fixed_bytes = int(d_clen.sum())
+        t0 = time.time()
+        eng.train_tree_device(d_src, BLOCK, None, BLOCK, min(n, 1 << 16), stream=stream)     # trained on the first 65536 blocks
+        t_train = time.time() - t0
+        tstride = eng.bound(BLOCK)
+        d_tc = torch.empty(n * tstride, dtype=torch.uint8, device=dev)
+
+        def run():
+            eng.compress_batch(d_src, BLOCK, None, BLOCK, d_tc, tstride, d_clen, d_st, n, stream=stream)
+        run()
+        torch.cuda.synchronize()
+        assert int(d_st.abs().sum()) == 0, "tree: status"
+        tree_bytes = int(d_clen.sum())
+        d_back = torch.empty(n * BLOCK, dtype=torch.uint8, device=dev)
+        d_blen = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_bst = torch.zeros(n, dtype=torch.int32, device=dev)
+        eng.decompress_batch(d_tc, None, tstride, d_clen, d_back, BLOCK, BLOCK, d_blen, d_bst, n,
+                             flags=hz.F_VERIFY_ADLER, stream=stream)
+        torch.cuda.synchronize()
+        assert int(d_bst.abs().sum()) == 0 and torch.equal(d_back, d_src.view(-1)), "tree: round trip"
+        ms, best = _time_launches(run, steps)
+        lit, dist = eng.tree
+        out[name] = {"compress_gbps": n * BLOCK / (ms * 1e-3) / 1e9, "ms": ms, "ratio_tree": tree_bytes / (n * BLOCK),
+                     "ratio_fixed": fixed_bytes / (n * BLOCK), "train_seconds": t_train,
+                     "max_code_bits": [int(lit.max()), int(dist.max())], "round_trip_verified": True}
+        del d_comp, d_tc, d_back
+        eng.set_tree()
+    out["what"] = ("hdlz_train_tree on the first 65536 blocks, then hdlz_compress_batch with the trained code (one "
+                   "BTYPE = 10 block per stream, the reference's parse) against the fixed code; n = %d blocks" % n)
+    return out
+
+
 def config4_plain(nd, L=32768, seed=4):
     """Plain side of configs[3]: Zipf-like bytes over 64 symbols with repeats at distances up to 32 KiB
     (SURVEY 8(d)); compressible enough that zlib level 6 emits dynamic blocks."""
@@ -650,6 +699,34 @@ def main():
         pool.shutdown()
         assert torch.equal(h_back, h_in)
         pk = int(total[0].value)
+        # the ceiling of this leg: raw pinned copies of the same payload bytes in both directions at once, all
+        # ranks at the same time (what the host's PCIe / memory system gives with no kernel and no pipeline)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        d_a = torch.empty(ne * BLOCK, dtype=torch.uint8, device=dev)
+        d_b = torch.empty(max(pk, 16), dtype=torch.uint8, device=dev)
+        hin, hback = h_in.view(-1), h_back.view(-1)
+        cb = 48 << 20
+
+        def raw_step():
+            with torch.cuda.stream(s_up):
+                for o in range(0, ne * BLOCK, cb):
+                    d_a[o:o + cb].copy_(hin[o:o + cb], non_blocking=True)
+                for o in range(0, pk, cb):
+                    d_b[o:min(o + cb, pk)].copy_(h_comp[0][o:min(o + cb, pk)], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                for o in range(0, ne * BLOCK, cb):
+                    hback[o:o + cb].copy_(d_a[o:o + cb], non_blocking=True)
+                for o in range(0, pk, cb):
+                    h_comp[1][o:min(o + cb, pk)].copy_(d_b[o:min(o + cb, pk)], non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+        raw_step()
+        sync_ranks()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            raw_step()
+        t_raw = max_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        del d_a, d_b
         h2d = ne * BLOCK + pk + (8 + 4) * ne                 # blocks; packed streams + offsets + lengths
         d2h = pk + (8 + 4 + 4) * ne + ne * BLOCK + (4 + 4) * ne
         e2e = {"value": 2 * ne * BLOCK * world / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
@@ -659,6 +736,10 @@ def main():
                       "host buffers, packed streams, chunked 3-stream pipelines); every step moves one full round trip",
                "back_to_back": {"value": 2 * ne * BLOCK * world / te_seq / 1e9, "ms_per_step": te_seq * 1e3,
                                 "api": "the same two calls one after the other on one context"},
+               "raw_copy_ceiling": {"value": 2 * ne * BLOCK * world / t_raw / 1e9, "ms_per_step": t_raw * 1e3,
+                                    "what": "cudaMemcpyAsync of the step's payload (blocks + packed streams up, packed "
+                                            "streams + blocks down) on two streams, 48 MiB pieces, no kernels: the same "
+                                            "metric if the host link were the only cost"},
                "note": "all %d ranks concurrently, max over ranks" % world}
         eng2.close()
         del h_in, h_comp, h_back
@@ -743,6 +824,7 @@ def main():
         cfgs["config3"] = run_config3(eng, hz, d_in, n, dev, stream, max(3, args.steps // 2), threads, peak)
         cfgs["config4"] = run_config4(eng, hz, args.c4_streams, min(args.c4_distinct, args.c4_streams), dev, stream,
                                       max(3, args.steps // 2), threads, peak)
+        cfgs["tree"] = run_tree(eng, hz, d_in, n, dev, stream, max(3, args.steps // 2))
         line["configs"] = cfgs
 
     print(json.dumps(line), flush=True)

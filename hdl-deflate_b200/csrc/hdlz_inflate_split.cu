@@ -41,7 +41,8 @@ constexpr int kDistBits = 7;
 constexpr int kLitBytes = (1 << kLitBits) * 64;               // entry i of lane l at i * 64 + 2 l
 constexpr int kDistBytes = (1 << kDistBits) * 32;             // entry i of lane l at kLitBytes + i * 32 + l (also the code-length-code table)
 constexpr int kTabBytes = kLitBytes + kDistBytes;             // 20 KiB per warp
-constexpr int kRingBytes = 1024;                              // input ring: two 16-byte vectors per lane
+constexpr int kRingSlots = 4;                                 // input ring: four 16-byte vectors per lane
+constexpr int kRingBytes = kRingSlots * 512;
 
 constexpr int kResThreads = 256;
 constexpr int kResCtasPerSm = 6;
@@ -131,9 +132,9 @@ __device__ __noinline__ int split_build(const uint8_t *lens, int nsym, LaneTab t
 // code longer than the primary table: canonical decode one bit at a time, starting after the `tbits`
 // bits the table has already ruled out.  -> (sym << 4) | len, 0 = invalid
 __device__ __forceinline__ uint32_t split_slow(uint32_t bits, unsigned long long beyond, int cbits, const uint16_t *sorted,
-                                               int tbits, const uint16_t *resume)
+                                               int tbits, uint32_t resume)
 {
-    int code = (int)((__brev(bits) >> (32 - tbits)) << 1), first = resume[0], index = resume[1];
+    int code = (int)((__brev(bits) >> (32 - tbits)) << 1), first = (int)(resume & 0xFFFFu), index = (int)(resume >> 16);
     for (int l = tbits + 1; l <= 15; ++l) {
         code |= (int)((bits >> (l - 1)) & 1u);
         const int c = (int)((beyond >> (cbits * (l - tbits - 1))) & ((1u << cbits) - 1u));
@@ -175,6 +176,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     uint8_t *wblock = reinterpret_cast<uint8_t *>(s_tab) + (size_t)(threadIdx.x >> 5) * kTabBytes;
     const LaneTab tab = {wblock + 2 * lane, wblock + kLitBytes + lane};
     unsigned long long beyond_l = 0, beyond_d = 0;          // codes per length beyond the tables (9..15 x 9 bits, 8..15 x 8 bits)
+    uint32_t res_l = 0, res_d = 0;                          // where the bit-serial decode resumes: first code | index << 16
     SplitScratch *my = scratch + ((size_t)blockIdx.x * (kDecWarps * 32) + threadIdx.x);
     // input ring of this lane: two slots of four words; slot s at ring[s * 128 .. +4) (16 bytes per lane, 512 per slot)
     uint32_t *ring = s_tab + (size_t)kDecWarps * (kTabBytes / 4) + (size_t)(threadIdx.x >> 5) * (kRingBytes / 4) + 4 * lane;
@@ -186,12 +188,15 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     const uint32_t *inw = reinterpret_cast<const uint32_t *>(in);
     uint32_t st = HDLZ_OK;
     uint32_t o = 0, final_blk = 0, stored_left = 0;
-    // bit reader: the stream bits from bit `p` of w0 on; w1, w2 follow.  Between symbols p < 32, so a 32-bit
-    // peek is one funnel shift and consuming is one add.  The words come out of a two-vector ring in shared
-    // memory that cp.async fills a whole 16-byte vector ahead — straight from global to shared memory, so no
-    // register waits for the load (a register prefetch was copied at every loop merge and stalled there).
-    uint32_t w0 = 0, w1 = 0, w2 = 0, wi = 0, p = 0;         // wi = stream word index of w0
-    uint32_t rp = 0, vi = 0, m4 = 0;                         // ring read position 0..7, next vector to fetch, (src & 15) / 4
+    // bit reader: the stream bits from bit `p` of w0 on; w1, w2, w3 follow.  Between trips p < 32; a trip of the
+    // block loop reads at most 104 bits past it, so the four words cover every peek of a trip with no refill
+    // in between, and ONE refill at the end of the trip — the same instructions for every lane, however many
+    // words (0..3) it moves on — replaces the per-symbol `if (p >= 32) advance()` that ran for a few lanes at a
+    // time (a quarter of the kernel's issue slots at 5 of 32 lanes, profiles/r02_decode_v4_regions.txt).  The
+    // words come out of a four-vector ring in shared memory that cp.async fills three vectors ahead, straight
+    // from global memory: the vector a lane reads was asked for at least two fetches ago.
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, wi = 0, p = 0;  // wi = stream word index of w0
+    uint32_t rc = 0, vf = 0, v0 = 0, m4 = 0;                 // ring words read, vectors fetched (both from vector v0 on), (src & 15) / 4
     uint32_t *tokp = tokbuf, *litp = litbuf;
     uint32_t ntok = 0, litw = 0, litfill = 0, pend = 0;
     uint64_t litacc = 0;
@@ -202,9 +207,9 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
         if (w >= 0 && w < (int64_t)nfull) v = __ldg(inw + w);
         return v;
     };
-    auto fetch_vec = [&](uint32_t v, uint32_t slot) {        // 16-byte aligned vector v (stream words 4 v - m4 ..) -> ring slot
-        const int64_t i0 = (int64_t)4 * v - m4;
-        uint32_t *dstw = ring + slot * 128;                  // this lane's four words of the slot
+    auto fetch_next = [&]() {                                // vector v0 + vf (stream words 4 (v0 + vf) - m4 ..) -> its ring slot
+        const int64_t i0 = (int64_t)4 * (v0 + vf) - m4;
+        uint32_t *dstw = ring + (vf & (kRingSlots - 1u)) * 128;   // this lane's four words of the slot
         if (i0 >= 0 && i0 + 4 <= (int64_t)nfull) {
             const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dstw);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(inw + i0) : "memory");
@@ -212,28 +217,39 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             dstw[0] = load_word(i0); dstw[1] = load_word(i0 + 1); dstw[2] = load_word(i0 + 2); dstw[3] = load_word(i0 + 3);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        ++vf;
     };
-    auto pop = [&]() -> uint32_t {
-        const uint32_t r = ring[(rp >> 2) * 128 + (rp & 3u)];
-        rp = (rp + 1u) & 7u;
-        if ((rp & 3u) == 0) {
-            // the slot just read is free: the vector after next goes there; the next one (asked for four words
-            // ago) must have landed before it is read
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fetch_vec(vi, (rp >> 2) ^ 1u);
-            ++vi;
-        }
-        return r;
+    auto ring_word = [&](uint32_t r) -> uint32_t { return ring[((r >> 2) & (kRingSlots - 1u)) * 128 + (r & 3u)]; };
+    // end of a block-loop trip: move on by p / 32 words (0..3), refill the window from the ring, keep the ring
+    // three vectors ahead.  No branch except the fetch itself (every fourth word of a lane).
+    auto refill = [&]() {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        const uint32_t n = p >> 5;
+        const uint32_t a = ring_word(rc), b = ring_word(rc + 1u), c = ring_word(rc + 2u);
+        const uint32_t t0 = n == 0u ? w0 : n == 1u ? w1 : n == 2u ? w2 : w3;
+        const uint32_t t1 = n == 0u ? w1 : n == 1u ? w2 : n == 2u ? w3 : a;
+        const uint32_t t2 = n == 0u ? w2 : n == 1u ? w3 : n == 2u ? a : b;
+        const uint32_t t3 = n == 0u ? w3 : n == 1u ? a : n == 2u ? b : c;
+        w0 = t0; w1 = t1; w2 = t2; w3 = t3;
+        rc += n;
+        wi += n;
+        p &= 31u;
+        if (vf < (rc >> 2) + kRingSlots) fetch_next();
     };
-    auto advance = [&]() {         // call when p >= 32
-        w0 = w1; w1 = w2;
-        w2 = pop();
+    // the other states (block headers, stored bytes): one word at a time, when p >= 32
+    auto advance = [&]() {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        w0 = w1; w1 = w2; w2 = w3;
+        w3 = ring_word(rc);
+        ++rc;
         ++wi;
         p -= 32u;
+        if (vf < (rc >> 2) + kRingSlots) fetch_next();
     };
     auto peek = [&]() -> uint32_t { return __funnelshift_r(w0, w1, p); };       // p < 32
-    auto peek_at = [&](uint32_t pp) -> uint32_t {                              // pp < 64
-        return __funnelshift_r(pp < 32u ? w0 : w1, pp < 32u ? w1 : w2, pp & 31u);
+    auto peek_at = [&](uint32_t pp) -> uint32_t {                              // pp < 96
+        const uint32_t k = pp >> 5;
+        return __funnelshift_r(k == 0u ? w0 : k == 1u ? w1 : w2, k == 0u ? w1 : k == 1u ? w2 : w3, pp & 31u);
     };
     auto bitpos = [&]() -> uint64_t { return (uint64_t)wi * 32u + p; };         // stream bits consumed
     auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
@@ -294,13 +310,16 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                             wi = frame.body >> 2;
                             p = 8u * (frame.body & 3u);
                             const uint32_t a = wi + m4;                          // aligned word index of the first word
-                            vi = a >> 2;
-                            fetch_vec(vi, 0);
-                            fetch_vec(vi + 1, 1);
-                            vi += 2;
+                            // nothing of the lane's previous stream may still be landing in the ring
                             asm volatile("cp.async.wait_group 0;" ::: "memory");
-                            rp = a & 3u;
-                            w0 = pop(); w1 = pop(); w2 = pop();
+                            v0 = a >> 2;
+                            vf = 0;
+                            for (int k = 0; k < kRingSlots; ++k) fetch_next();
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            rc = a & 3u;
+                            w0 = ring_word(rc); w1 = ring_word(rc + 1u); w2 = ring_word(rc + 2u); w3 = ring_word(rc + 3u);
+                            rc += 4u;
+                            if (vf < (rc >> 2) + kRingSlots) fetch_next();
                         }
                     }
                 }
@@ -315,7 +334,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
             if (wi > nfull + 4) fail(HDLZ_ST_TRUNCATED);          // far past the end of the input: a runaway decode
             else {
                 {
-                    const uint32_t x = peek();
+                    const uint32_t x = peek();                              // p < 32 here; nothing below moves the window
                     const uint32_t room = out_cap - o;
                     uint32_t used = 0, nl = 0, lw = 0;
                     bool go = true;
@@ -342,16 +361,15 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         tokp[ntok++] = pend;
                         pend = 0;
                     }
-                    if (p >= 32u) advance();
                 }
-                const uint32_t x = peek();
+                const uint32_t x = peek_at(p);                              // p < 56
                 const uint32_t e = tab.get_lit(x & ((1u << kLitBits) - 1u));
                 const uint32_t nb = e & 15u, ls = (e >> 4) - 257u;
                 const bool is_len = ls < 29u && nb != 0u;                     // a length symbol of the table
                 const uint32_t info = s_len[is_len ? ls : 0u];
                 const uint32_t eb = info & 15u;
                 const uint32_t len = (info >> 16) + ((x >> nb) & ((1u << eb) - 1u));    // <= 8 + 5 bits of 32
-                const uint32_t p2 = p + nb + eb;                                // < 32 + 13
+                const uint32_t p2 = p + nb + eb;                                // < 56 + 13
                 const uint32_t y = peek_at(p2);
                 const uint32_t d = tab.get_dist(y & ((1u << kDistBits) - 1u));
                 const uint32_t dnb = d & 7u, dsym = d >> 3;
@@ -360,16 +378,14 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 const uint32_t dist = (de >> 8) + ((y >> dnb) & ((1u << deb) - 1u));   // <= 7 + 13 bits of 32
                 const bool copy = is_len && dnb != 0u && dsym < 30u && dist <= o && len <= out_cap - o;
                 if (copy) {
-                    p = p2 + dnb + deb;                                         // < 45 + 20
+                    p = p2 + dnb + deb;                                         // < 69 + 20
                     tokp[ntok++] = pend | (len << 8) | ((dist - 1u) << 17);
                     pend = 0;
                     o += len;
-                    if (p >= 32u) advance();
-                    if (p >= 32u) advance();
                 } else if (e >= (256u << 4) || o >= out_cap) {
                     // ---- `other`: not a copy the tables decode, and not a literal the next trip takes
                     uint32_t e2 = e;
-                    if ((e2 & 15u) == 0) e2 = split_slow(x, beyond_l, 9, my->sorted_l, kLitBits, my->resume_l);
+                    if ((e2 & 15u) == 0) e2 = split_slow(x, beyond_l, 9, my->sorted_l, kLitBits, res_l);
                     const uint32_t nb2 = e2 & 15u, sym = e2 >> 4;
                     if (nb2 == 0) {
                         fail(HDLZ_ST_BAD_CODE);                                 // no such code ("Invalid data")
@@ -386,12 +402,11 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         const uint32_t info2 = s_len[sym - 257u];
                         const uint32_t eb2 = info2 & 15u;
                         const uint32_t len2 = (info2 >> 16) + ((x >> nb2) & ((1u << eb2) - 1u));    // <= 15 + 5 bits of 32
-                        p += nb2 + eb2;
-                        if (p >= 32u) advance();
-                        const uint32_t y2 = peek();
+                        p += nb2 + eb2;                                         // < 56 + 20
+                        const uint32_t y2 = peek_at(p);
                         const uint32_t dq = tab.get_dist(y2 & ((1u << kDistBits) - 1u));
                         uint32_t d2 = ((dq >> 3) << 4) | (dq & 7u);                  // -> (symbol << 4 | length)
-                        if ((d2 & 15u) == 0) d2 = split_slow(y2, beyond_d, 8, my->sorted_d, kDistBits, my->resume_d);
+                        if ((d2 & 15u) == 0) d2 = split_slow(y2, beyond_d, 8, my->sorted_d, kDistBits, res_d);
                         const uint32_t dnb2 = d2 & 15u;
                         if (dnb2 == 0 || (d2 >> 4) >= 30u) {
                             fail(HDLZ_ST_BAD_CODE);
@@ -409,8 +424,8 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                             }
                         }
                     }
-                    if (p >= 32u) advance();
                 }
+                refill();                                                   // p < 76 + 28: at most three words
             }
         } else if (state == S_HEADER) {
             const bool past_end = bitpos() + 3 > 8ull * n_in;
@@ -459,7 +474,8 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     for (uint32_t i = 0; i < ncode; ++i) lens[c_clorder[i]] = (uint8_t)get(3);
                     // code-length code: 7-bit table in the distance table's place, its arrays in the distance code's;
                     // it must be complete and not empty (zlib: "invalid code lengths set")
-                    if (!bad) bad = split_build<false>(lens, 19, tab, 7, 8, my->sorted_d, my->resume_d, false, &beyond_d) ? 1u : 0u;
+                    unsigned long long bt = 0;
+                    if (!bad) bad = split_build<false>(lens, 19, tab, 7, 8, my->sorted_d, my->resume_d, false, &bt) ? 1u : 0u;
                     uint32_t idx = 0, prev = 0;
                     const uint32_t total = nlen + ndist;
                     while (!bad && idx < total) {
@@ -483,8 +499,13 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                     if (!bad && lens[256] == 0) bad = 1;                         // no end-of-block code
                 }
                 // an empty distance code is legal (a block of literals only): any use of it fails later
-                if (!bad) bad = split_build<false>(lens + nlen, (int)ndist, tab, kDistBits, 8, my->sorted_d, my->resume_d, true, &beyond_d) == 1 ? 1u : 0u;
-                if (!bad) bad = split_build<true>(lens, (int)nlen, tab, kLitBits, 9, my->sorted_l, my->resume_l, true, &beyond_l) == 1 ? 1u : 0u;
+                unsigned long long bd = 0, bl = 0;
+                if (!bad) bad = split_build<false>(lens + nlen, (int)ndist, tab, kDistBits, 8, my->sorted_d, my->resume_d, true, &bd) == 1 ? 1u : 0u;
+                if (!bad) bad = split_build<true>(lens, (int)nlen, tab, kLitBits, 9, my->sorted_l, my->resume_l, true, &bl) == 1 ? 1u : 0u;
+                beyond_d = bd;
+                beyond_l = bl;
+                res_d = (uint32_t)my->resume_d[0] | ((uint32_t)my->resume_d[1] << 16);
+                res_l = (uint32_t)my->resume_l[0] | ((uint32_t)my->resume_l[1] << 16);
                 if (bad) fail(bad == 2 ? HDLZ_ST_TRUNCATED : HDLZ_ST_BAD_CODE);   // "Invalid data" (deflate.py:1140)
                 else state = S_BLOCK;
             }

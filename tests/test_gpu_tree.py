@@ -137,8 +137,11 @@ def test_long_stream_and_worst_case_bound(eng):
     got = eng.compress(data)
     st, want = T.compress(data, list(lit), list(dist))
     assert st == 0 and got == want and zlib.decompress(got) == data
-    # skewed counts: byte 0 takes almost everything, the other 255 literals end up with long codes
-    cnt = [1 << 40] + [1] * 255 + [1 << 30] + [1 << 20] * 8 + [0] * 21
+    # Fibonacci counts: the code hits the 15-bit limit
+    fib = [1, 1]
+    while len(fib) < 60:
+        fib.append(fib[-1] + fib[-2])
+    cnt = [fib[59 - (s % 60)] for s in range(256)] + [1 << 30] + [1 << 20] * 8 + [0] * 21
     lit = T.limited_lengths(cnt, 15)
     assert max(lit) == 15
     dist = T.limited_lengths([1] * 10 + [0] * 20, 15)
