@@ -147,6 +147,22 @@ __device__ __forceinline__ uint32_t split_slow(uint32_t bits, unsigned long long
     return 0;
 }
 
+// The same search without the final look-up: (position in `sorted` << 4) | length, 0 = no such code.  Registers only.
+__device__ __forceinline__ uint32_t split_slow_find(uint32_t bits, unsigned long long beyond, int cbits, int tbits, uint32_t resume)
+{
+    int code = (int)((__brev(bits) >> (32 - tbits)) << 1), first = (int)(resume & 0xFFFFu), index = (int)(resume >> 16);
+    for (int l = tbits + 1; l <= 15; ++l) {
+        code |= (int)((bits >> (l - 1)) & 1u);
+        const int c = (int)((beyond >> (cbits * (l - tbits - 1))) & ((1u << cbits) - 1u));
+        if (code - c < first) return ((uint32_t)(index + (code - first)) << 4) | (uint32_t)l;
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return 0;
+}
+
 // literal/length symbol 257..285 -> extra bits (0..5) | base length << 16
 __device__ __forceinline__ uint32_t len_entry(uint32_t sym) { return (uint32_t)c_lextra[sym - 257] | ((uint32_t)c_lbase[sym - 257] << 16); }
 // distance symbol 0..29 -> extra bits (0..13) | base distance << 8
@@ -167,6 +183,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     extern __shared__ uint32_t s_tab[];                     // [kDecWarps] table blocks, then the input rings
     __shared__ uint32_t s_len[32];                          // length symbol - 257 -> len_entry
     __shared__ uint32_t s_dsym[32];                         // distance symbol -> dist_entry
+    __shared__ uint32_t s_slow[kDecWarps * 32];             // per lane: the word of `sorted` a long code asked for (see slow_issue)
     if (threadIdx.x < 29) s_len[threadIdx.x] = len_entry(257 + threadIdx.x);
     if (threadIdx.x < 32) s_dsym[threadIdx.x] = threadIdx.x < 30 ? dist_entry(threadIdx.x) : 0u;
     __syncthreads();
@@ -194,9 +211,9 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     // words (0..3) it moves on — replaces the per-symbol `if (p >= 32) advance()` that ran for a few lanes at a
     // time (a quarter of the kernel's issue slots at 5 of 32 lanes, profiles/r02_decode_v4_regions.txt).  The
     // words come out of a four-vector ring in shared memory that cp.async fills three vectors ahead, straight
-    // from global memory: the vector a lane reads was asked for at least two fetches ago.
+    // from global memory: the vectors a lane reads were asked for at least one fetch before the newest.
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, wi = 0, p = 0;  // wi = stream word index of w0
-    uint32_t rc = 0, vf = 0, v0 = 0, m4 = 0;                 // ring words read, vectors fetched (both from vector v0 on), (src & 15) / 4
+    uint32_t rc = 0, vf = 0, v0 = 0, m4 = 0;                 // ring index of w0, vectors fetched (both from vector v0 on), (src & 15) / 4
     uint32_t *tokp = tokbuf, *litp = litbuf;
     uint32_t ntok = 0, litw = 0, litfill = 0, pend = 0;
     uint64_t litacc = 0;
@@ -222,34 +239,51 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
     auto ring_word = [&](uint32_t r) -> uint32_t { return ring[((r >> 2) & (kRingSlots - 1u)) * 128 + (r & 3u)]; };
     // end of a block-loop trip: move on by p / 32 words (0..3), refill the window from the ring, keep the ring
     // three vectors ahead.  No branch except the fetch itself (every fourth word of a lane).
+    // (the window is simply read again from the ring at its new place: four loads, no word shuffling)
     auto refill = [&]() {
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        // all but the newest fetch have landed: vf - 1 is at least two vectors past the window's first, the window
+        // (rc .. rc + 3) reaches into the next vector at most
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         const uint32_t n = p >> 5;
-        const uint32_t a = ring_word(rc), b = ring_word(rc + 1u), c = ring_word(rc + 2u);
-        const uint32_t t0 = n == 0u ? w0 : n == 1u ? w1 : n == 2u ? w2 : w3;
-        const uint32_t t1 = n == 0u ? w1 : n == 1u ? w2 : n == 2u ? w3 : a;
-        const uint32_t t2 = n == 0u ? w2 : n == 1u ? w3 : n == 2u ? a : b;
-        const uint32_t t3 = n == 0u ? w3 : n == 1u ? a : n == 2u ? b : c;
-        w0 = t0; w1 = t1; w2 = t2; w3 = t3;
         rc += n;
         wi += n;
         p &= 31u;
-        if (vf < (rc >> 2) + kRingSlots) fetch_next();
+        w0 = ring_word(rc); w1 = ring_word(rc + 1u); w2 = ring_word(rc + 2u); w3 = ring_word(rc + 3u);
+        if (vf < (rc >> 2) + kRingSlots) fetch_next();            // the vector left behind gives its slot to the next one
     };
     // the other states (block headers, stored bytes): one word at a time, when p >= 32
     auto advance = [&]() {
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
-        w0 = w1; w1 = w2; w2 = w3;
-        w3 = ring_word(rc);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         ++rc;
         ++wi;
         p -= 32u;
+        w0 = w1; w1 = w2; w2 = w3;
+        w3 = ring_word(rc + 3u);
         if (vf < (rc >> 2) + kRingSlots) fetch_next();
     };
     auto peek = [&]() -> uint32_t { return __funnelshift_r(w0, w1, p); };       // p < 32
     auto peek_at = [&](uint32_t pp) -> uint32_t {                              // pp < 96
         const uint32_t k = pp >> 5;
         return __funnelshift_r(k == 0u ? w0 : k == 1u ? w1 : w2, k == 0u ? w1 : k == 1u ? w2 : w3, pp & 31u);
+    };
+    // A code longer than its table ends in a look-up in the lane's sorted-symbols array in global memory, and a
+    // warp meets one in every second trip: waiting for that load held all 32 lanes for an L2 round trip.  The
+    // lane now only ASKS for the word (cp.async into its slot of s_slow) and makes no progress in this trip;
+    // the next trip arrives at the same code again and takes the symbol from shared memory, the load having
+    // travelled while the other lanes decoded.  slow_kind: 0 nothing asked, 1 literal/length, 2 distance.
+    uint32_t slow_kind = 0, slow_meta = 0;                   // meta: code length | (index & 1) << 4
+    auto slow_issue = [&](uint32_t found, const uint16_t *sorted) {
+        const uint32_t idx = found >> 4;
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&s_slow[threadIdx.x]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\ncp.async.commit_group;"
+                     ::"r"(sa), "l"(reinterpret_cast<const uint32_t *>(sorted) + (idx >> 1)) : "memory");
+        slow_meta = (found & 15u) | ((idx & 1u) << 4);
+    };
+    auto slow_take = [&]() -> uint32_t {                     // -> (symbol << 4) | length
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint32_t w = *reinterpret_cast<volatile uint32_t *>(&s_slow[threadIdx.x]);
+        slow_kind = 0;
+        return (((w >> (16u * (slow_meta >> 4))) & 0xFFFFu) << 4) | (slow_meta & 15u);
     };
     auto bitpos = [&]() -> uint64_t { return (uint64_t)wi * 32u + p; };         // stream bits consumed
     auto fail = [&](uint32_t code) { st = code; state = S_FINISH; };
@@ -298,6 +332,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         litp = litbuf + (size_t)item * litcap_words;
                         st = HDLZ_OK;
                         o = 0; ntok = 0; litw = 0; litfill = 0; pend = 0; litacc = 0;
+                        slow_kind = 0;
                         final_blk = 0; stored_left = 0;
                         state = S_HEADER;
                         const Frame frame = parse_frame(src, n_in, flags);
@@ -318,8 +353,6 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                             asm volatile("cp.async.wait_group 0;" ::: "memory");
                             rc = a & 3u;
                             w0 = ring_word(rc); w1 = ring_word(rc + 1u); w2 = ring_word(rc + 2u); w3 = ring_word(rc + 3u);
-                            rc += 4u;
-                            if (vf < (rc >> 2) + kRingSlots) fetch_next();
                         }
                     }
                 }
@@ -362,7 +395,7 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         pend = 0;
                     }
                 }
-                const uint32_t x = peek_at(p);                              // p < 56
+                const uint32_t x = __funnelshift_r(p < 32u ? w0 : w1, p < 32u ? w1 : w2, p & 31u);   // p < 56
                 const uint32_t e = tab.get_lit(x & ((1u << kLitBits) - 1u));
                 const uint32_t nb = e & 15u, ls = (e >> 4) - 257u;
                 const bool is_len = ls < 29u && nb != 0u;                     // a length symbol of the table
@@ -385,9 +418,23 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                 } else if (e >= (256u << 4) || o >= out_cap) {
                     // ---- `other`: not a copy the tables decode, and not a literal the next trip takes
                     uint32_t e2 = e;
-                    if ((e2 & 15u) == 0) e2 = split_slow(x, beyond_l, 9, my->sorted_l, kLitBits, res_l);
+                    const bool lit_long = (e2 & 15u) == 0;
+                    bool defer = false;                      // asked for a symbol: this trip ends here for the lane
+                    if (lit_long) {
+                        if (slow_kind == 1u) {
+                            e2 = slow_take();
+                        } else {
+                            const uint32_t found = split_slow_find(x, beyond_l, 9, kLitBits, res_l);
+                            if (found) {
+                                slow_issue(found, my->sorted_l);
+                                slow_kind = 1u;
+                                defer = true;
+                            }
+                        }
+                    }
                     const uint32_t nb2 = e2 & 15u, sym = e2 >> 4;
-                    if (nb2 == 0) {
+                    if (defer) {
+                    } else if (nb2 == 0) {
                         fail(HDLZ_ST_BAD_CODE);                                 // no such code ("Invalid data")
                     } else if (sym < 256u) {
                         if (o >= out_cap) fail(HDLZ_ST_OUT_OVERFLOW);
@@ -402,19 +449,34 @@ k_decode_tokens(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_
                         const uint32_t info2 = s_len[sym - 257u];
                         const uint32_t eb2 = info2 & 15u;
                         const uint32_t len2 = (info2 >> 16) + ((x >> nb2) & ((1u << eb2) - 1u));    // <= 15 + 5 bits of 32
-                        p += nb2 + eb2;                                         // < 56 + 20
-                        const uint32_t y2 = peek_at(p);
+                        const uint32_t pd = p + nb2 + eb2;                      // < 56 + 20
+                        const uint32_t y2 = peek_at(pd);
                         const uint32_t dq = tab.get_dist(y2 & ((1u << kDistBits) - 1u));
                         uint32_t d2 = ((dq >> 3) << 4) | (dq & 7u);                  // -> (symbol << 4 | length)
-                        if ((d2 & 15u) == 0) d2 = split_slow(y2, beyond_d, 8, my->sorted_d, kDistBits, res_d);
+                        if ((d2 & 15u) == 0) {
+                            if (lit_long) {
+                                // both codes longer than their tables: this one waits for its symbol
+                                d2 = split_slow(y2, beyond_d, 8, my->sorted_d, kDistBits, res_d);
+                            } else if (slow_kind == 2u) {
+                                d2 = slow_take();
+                            } else {
+                                const uint32_t found = split_slow_find(y2, beyond_d, 8, kDistBits, res_d);
+                                if (found) {
+                                    slow_issue(found, my->sorted_d);
+                                    slow_kind = 2u;
+                                    defer = true;                               // the length symbol is decoded again next trip
+                                }
+                            }
+                        }
                         const uint32_t dnb2 = d2 & 15u;
-                        if (dnb2 == 0 || (d2 >> 4) >= 30u) {
+                        if (defer) {
+                        } else if (dnb2 == 0 || (d2 >> 4) >= 30u) {
                             fail(HDLZ_ST_BAD_CODE);
                         } else {
                             const uint32_t de2 = s_dsym[d2 >> 4];
                             const uint32_t deb2 = de2 & 15u;
                             const uint32_t dist2 = (de2 >> 8) + ((y2 >> dnb2) & ((1u << deb2) - 1u));   // <= 15 + 13 bits
-                            p += dnb2 + deb2;
+                            p = pd + dnb2 + deb2;
                             if (dist2 > o) fail(HDLZ_ST_DIST_TOO_FAR);           // "distance too big" (deflate.py:1506-1508)
                             else if (len2 > out_cap - o) fail(HDLZ_ST_OUT_OVERFLOW);
                             else {

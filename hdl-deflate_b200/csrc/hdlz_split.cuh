@@ -10,7 +10,7 @@ constexpr uint32_t kSplitMaxOut = 32768;       // phase 2 stages a whole stream'
 
 // per resident decoder thread, global memory: what the rare paths of phase 1 need (code lengths while a block
 // header is parsed, sorted symbols + resume point of the bit-serial decode of codes longer than the tables)
-struct SplitScratch {
+struct alignas(8) SplitScratch {          // sorted_l / sorted_d are read as 32-bit words by the decoder
     uint16_t sorted_l[288];
     uint16_t sorted_d[32];
     uint16_t resume_l[2];
