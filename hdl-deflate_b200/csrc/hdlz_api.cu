@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "hdlz_common.cuh"
@@ -51,7 +52,7 @@ int grow_device(void **p, size_t *cap, size_t need)
 
 static int ensure_pipe(hdlz_ctx *ctx)
 {
-    for (int i = 0; i < kHostPipe; i++)
+    for (int i = 0; i < ctx->host_pipe; i++)
         if (!ctx->pipe[i]) {
             cudaError_t e = cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking);
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(pipe)");
@@ -102,7 +103,7 @@ static int check_lengths(const uint32_t *len, uint64_t n, uint64_t stride, bool 
 // error exit of a chunked pipeline: nothing may still be copying into the caller's buffers
 static int drain(hdlz_ctx *ctx, int rc)
 {
-    for (int i = 0; i < kHostPipe; i++)
+    for (int i = 0; i < kHostPipeMax; i++)
         if (ctx->pipe[i]) cudaStreamSynchronize(ctx->pipe[i]);
     return rc;
 }
@@ -164,6 +165,11 @@ int hdlz_create(int device, hdlz_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     c->max_match = HDLZ_MAX_MATCH;
     c->window = HDLZ_CWINDOW;
+    c->host_pipe = kHostPipe;
+    if (const char *e = getenv("HDLZ_HOST_PIPE")) {      // tuning knob of the *_host pipelines (tools/, profiles/)
+        const int v = atoi(e);
+        if (v >= 2 && v <= kHostPipeMax) c->host_pipe = v;
+    }
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -182,7 +188,7 @@ int hdlz_destroy(hdlz_ctx *c)
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
-    for (int i = 0; i < kHostPipe; i++)
+    for (int i = 0; i < kHostPipeMax; i++)
         if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_out) cudaFree(c->d_out);
@@ -267,6 +273,32 @@ int hdlz_decompress_batch(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
                           flags, 0, (cudaStream_t)stream);
 }
 
+// The *_host pipelines.  A batch is cut into ~48 MB chunks that go round ctx->host_pipe streams: copy-in of one
+// chunk, the kernels of the previous and copy-out of the one before overlap.  What the link is given besides the
+// payload decides the rate (tools/pcie_pattern.py: the payload of a 2^20-block round trip alone takes 70-72 ms;
+// four small copies per chunk add 11 ms, six streams per call instead of two or three another 8): per-stream
+// arrays (lengths, offsets, status words) cross once per call, not once per chunk, a stream is given its next
+// chunk only when its previous one is done, and the one small copy a chunk of the packed path needs (its packed
+// size and offsets) lands in a pinned staging area of the context.
+static int copy_in_lengths(hdlz_ctx *ctx, uint32_t *d_len, const uint32_t *in_len, uint64_t *d_off, const uint64_t *in_off, uint64_t n)
+{
+    cudaStream_t s = ctx->pipe[0];
+    if (in_len) HDLZ_CUDA(cudaMemcpyAsync(d_len, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (in_off) HDLZ_CUDA(cudaMemcpyAsync(d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (in_len || in_off) HDLZ_CUDA(cudaStreamSynchronize(s));      // the other streams' kernels read them
+    return HDLZ_SUCCESS;
+}
+
+static int copy_out_results(hdlz_ctx *ctx, uint32_t *out_len, const uint32_t *d_olen, uint32_t *status, const uint32_t *d_st, uint64_t n)
+{
+    for (int i = 0; i < ctx->host_pipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    cudaStream_t s = ctx->pipe[0];
+    HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len, d_olen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (status) HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status, d_st, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
+    return HDLZ_SUCCESS;
+}
+
 int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, const uint32_t *in_len,
                        uint32_t uniform_len, uint8_t *out, uint64_t out_stride, uint32_t *out_len,
                        uint32_t *status, uint64_t n)
@@ -282,28 +314,23 @@ int hdlz_compress_host(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stride, con
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
     uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
     if ((rc = ensure_pipe(ctx))) return rc;
-    // chunked three-stream pipeline: copy-in of chunk k+1, kernel of chunk k and copy-out of chunk k-1 overlap
+    if ((rc = copy_in_lengths(ctx, d_len, in_len, nullptr, nullptr, n))) return rc;
     const uint64_t chunk = host_chunk(n, in_stride + out_stride);
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
-        cudaStream_t s = ctx->pipe[k % kHostPipe];
+        cudaStream_t s = ctx->pipe[k % ctx->host_pipe];
+        if (k >= ctx->host_pipe) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
         HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                   cudaMemcpyHostToDevice, s));
-        if (in_len)
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         rc = hdlz_compress_batch(ctx, ctx->d_in + first * in_stride, in_stride, in_len ? d_len + first : nullptr,
                                  uniform_len, ctx->d_out + first * out_stride, out_stride, d_olen + first, d_st + first,
                                  m, s);
         if (rc) return drain(ctx, rc);
         HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
                                   cudaMemcpyDeviceToHost, s));
-        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (status)
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < kHostPipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
-    return HDLZ_SUCCESS;
+    return copy_out_results(ctx, out_len, d_olen, status, d_st, n);
 }
 
 int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint64_t in_stride,
@@ -332,43 +359,37 @@ int hdlz_decompress_host(hdlz_ctx *ctx, const uint8_t *in, const uint64_t *in_of
     if (in_off && (rc = grow((void **)&ctx->d_off, &ctx->d_off_cap, n * sizeof(uint64_t)))) return rc;
     uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
     if ((rc = ensure_pipe(ctx))) return rc;
-    // chunked three-stream pipeline (as hdlz_compress_host).  Packed input is chunked too when its
-    // offsets ascend (what hdlz_pack_batch produces); otherwise it goes in one piece.
+    if ((rc = copy_in_lengths(ctx, d_len, in_len, ctx->d_off, in_off, n))) return rc;
+    // Packed input is chunked too when its offsets ascend (what hdlz_pack_batch produces); otherwise it goes
+    // in one piece.
     bool ascending = true;
     if (in_off)
         for (uint64_t i = 1; i < n && ascending; i++) ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1];
     const uint64_t chunk = (in_off && !ascending) ? n : host_chunk(n, (in_off ? in_bytes / n + 1 : in_stride) + out_stride);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
-    (void)nchunks;
     int k = 0;
     for (uint64_t first = 0; first < n; first += chunk, ++k) {
         const uint64_t m = n - first < chunk ? n - first : chunk;
-        cudaStream_t s = ctx->pipe[k % kHostPipe];
-        // at most kHostPipe chunks are queued: a second call running beside this one (another context, another
-        // host thread) gets its copies into the copy engines' queues between ours instead of behind all of them
-        if (k >= kHostPipe) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
+        cudaStream_t s = ctx->pipe[k % ctx->host_pipe];
+        // a stream gets its next chunk when its previous one is done: a second call running beside this one (another
+        // context, another host thread) finds room in the copy engines' queues between ours instead of behind them
+        if (k >= ctx->host_pipe) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
         if (in_off) {
             const uint64_t lo = (nchunks == 1 ? 0 : in_off[first]) & ~(uint64_t)15;
             const uint64_t hi = nchunks == 1 ? in_bytes : in_off[first + m - 1] + in_len[first + m - 1];
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, s));
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_off + first, in_off + first, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         } else {
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
-                                      cudaMemcpyHostToDevice, s));
+                                  cudaMemcpyHostToDevice, s));
         }
-        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         rc = launch_inflate(ctx, in_off ? ctx->d_in : ctx->d_in + first * in_stride, in_off ? ctx->d_off + first : nullptr,
                             in_stride, d_len + first, ctx->d_out + first * out_stride, out_stride, out_cap,
                             d_olen + first, d_st + first, m, flags, k % 3, s);
         if (rc) return drain(ctx, rc);
         HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + first * out_stride, ctx->d_out + first * out_stride, m * out_stride,
                                   cudaMemcpyDeviceToHost, s));
-        HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (status)
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < kHostPipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
-    return HDLZ_SUCCESS;
+    return copy_out_results(ctx, out_len, d_olen, status, d_st, n);
 }
 
 int hdlz_pack_batch(hdlz_ctx *ctx, const uint8_t *d_slots, uint64_t stride, const uint32_t *d_len, uint8_t *d_packed,
@@ -402,64 +423,59 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
     const uint64_t slot = ctx->tree_set ? tree_bound(ctx, maxlen) : compress_bound(maxlen, ctx->container);
     const uint64_t chunk = host_chunk(n, in_stride + slot);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
+    // per chunk c, contiguous on the device and in the pinned staging area: [packed size | chunk-local offsets]
+    // at word first(c) + c
+    const size_t meta_words = (size_t)n + nchunks;
     if ((rc = grow((void **)&ctx->d_in, &ctx->d_in_cap, (size_t)n * in_stride))) return rc;
     if ((rc = grow((void **)&ctx->d_out, &ctx->d_out_cap, (size_t)n * slot))) return rc;
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint32_t)))) return rc;
-    if ((rc = grow((void **)&ctx->d_pack, &ctx->d_pack_cap, (size_t)n * slot + (n + nchunks + 2) * sizeof(uint64_t))))
-        return rc;
-    if (nchunks + 1 > ctx->h_small_cap) {
+    if ((rc = grow((void **)&ctx->d_pack, &ctx->d_pack_cap, (size_t)n * slot + 16 + meta_words * sizeof(uint64_t)))) return rc;
+    if (meta_words > ctx->h_small_cap) {
         if (ctx->h_small) cudaFreeHost(ctx->h_small);
         ctx->h_small = nullptr;
         ctx->h_small_cap = 0;
-        HDLZ_CUDA(cudaMallocHost((void **)&ctx->h_small, (nchunks + 64) * sizeof(uint64_t)));
-        ctx->h_small_cap = nchunks + 64;
+        HDLZ_CUDA(cudaMallocHost((void **)&ctx->h_small, (meta_words + meta_words / 4 + 64) * sizeof(uint64_t)));
+        ctx->h_small_cap = meta_words + meta_words / 4 + 64;
     }
     if ((rc = ensure_pipe(ctx))) return rc;
     uint32_t *d_len = ctx->d_meta, *d_olen = ctx->d_meta + n, *d_st = ctx->d_meta + 2 * n;
     uint8_t *d_packed = ctx->d_pack;                                               // chunk c packs into its slot range
-    uint64_t *d_off = reinterpret_cast<uint64_t *>(ctx->d_pack + (((size_t)n * slot + 15) & ~(size_t)15));
-    uint64_t *d_tot = d_off + n;
-    uint64_t *h_tot = ctx->h_small;
+    uint64_t *d_meta2 = reinterpret_cast<uint64_t *>(ctx->d_pack + (((size_t)n * slot + 15) & ~(size_t)15));
+    uint64_t *h_meta2 = ctx->h_small;
+    if ((rc = copy_in_lengths(ctx, d_len, in_len, nullptr, nullptr, n))) return rc;
     uint64_t base = 0;
-    // stage 1 (copy in, compress, pack, small copies out) of chunk c is enqueued kLag chunks ahead of
-    // stage 2 (packed bytes out), which needs the chunk's packed size on the host
-    constexpr uint64_t kLag = kHostPipe - 1;
+    // stage 1 (copy in, compress, pack, the chunk's size and offsets out) of chunk c is enqueued kLag chunks ahead
+    // of stage 2 (packed bytes out), which needs the chunk's packed size on the host
+    const uint64_t kLag = (uint64_t)ctx->host_pipe - 1;
     for (uint64_t c = 0; c < nchunks + kLag; ++c) {
         if (c < nchunks) {
             const uint64_t first = c * chunk, m = n - first < chunk ? n - first : chunk;
-            cudaStream_t s = ctx->pipe[c % kHostPipe];
+            cudaStream_t s = ctx->pipe[c % ctx->host_pipe];
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(ctx->d_in + first * in_stride, in + first * in_stride, m * in_stride,
                                       cudaMemcpyHostToDevice, s));
-            if (in_len)
-                HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(d_len + first, in_len + first, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             rc = hdlz_compress_batch(ctx, ctx->d_in + first * in_stride, in_stride, in_len ? d_len + first : nullptr,
                                      uniform_len, ctx->d_out + first * slot, slot, d_olen + first, d_st + first, m, s);
             if (rc) return drain(ctx, rc);
-            rc = launch_pack(ctx, ctx->d_out + first * slot, slot, d_olen + first, d_packed + first * slot, d_off + first,
-                             d_tot + c, m, s);
+            uint64_t *dm = d_meta2 + first + c;
+            rc = launch_pack(ctx, ctx->d_out + first * slot, slot, d_olen + first, d_packed + first * slot, dm + 1, dm, m, s);
             if (rc) return drain(ctx, rc);
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(h_tot + c, d_tot + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_off + first, d_off + first, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out_len + first, d_olen + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            if (status)
-                HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(status + first, d_st + first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(h_meta2 + first + c, dm, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         }
         if (c >= kLag) {
             const uint64_t cc = c - kLag, first = cc * chunk, m = n - first < chunk ? n - first : chunk;
-            cudaStream_t s = ctx->pipe[cc % kHostPipe];
+            cudaStream_t s = ctx->pipe[cc % ctx->host_pipe];
             HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(s));
-            const uint64_t tot = h_tot[cc];
-            if (base + tot > out_cap) {
-                for (int i = 0; i < kHostPipe; i++) cudaStreamSynchronize(ctx->pipe[i]);
-                return set_error(HDLZ_ERR_INVALID, "packed output needs more than out_cap = %llu bytes",
-                                 (unsigned long long)out_cap);
-            }
+            const uint64_t *hm = h_meta2 + first + cc;
+            const uint64_t tot = hm[0];
+            if (base + tot > out_cap)
+                return drain(ctx, set_error(HDLZ_ERR_INVALID, "packed output needs more than out_cap = %llu bytes",
+                                            (unsigned long long)out_cap));
             HDLZ_CUDA_DRAIN(ctx, cudaMemcpyAsync(out + base, d_packed + first * slot, tot, cudaMemcpyDeviceToHost, s));
-            for (uint64_t i = first; i < first + m; i++) out_off[i] += base;      // chunk-local -> global offsets
+            for (uint64_t i = 0; i < m; i++) out_off[first + i] = hm[1 + i] + base;     // chunk-local -> global offsets
             base += tot;
         }
     }
-    for (int i = 0; i < kHostPipe; i++) HDLZ_CUDA_DRAIN(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    if ((rc = copy_out_results(ctx, out_len, d_olen, status, d_st, n))) return rc;
     if (out_total) *out_total = base;
     return HDLZ_SUCCESS;
 }

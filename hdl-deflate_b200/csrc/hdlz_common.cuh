@@ -79,7 +79,8 @@ struct hdlz_ctx {
     uint32_t *h_dyn_seen;  // pinned [3]: dynamic-block streams the slot's last launch saw -> sizes the pool of the next one
     bool split_attr_set;
     cudaStream_t stream;  // owned, used by the host-buffer entry points
-    cudaStream_t pipe[6];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls (kHostPipe)
+    cudaStream_t pipe[6];  // owned, created on first use: chunked H2D / kernel / D2H pipeline of the *_host calls
+    int host_pipe;         // how many of them the pipelines use (kHostPipe; HDLZ_HOST_PIPE overrides)
     unsigned long long launches;
     // per-context launch state (was function-static: two contexts / threads raced on it)
     bool compress_attr_set;   // cudaFuncSetAttribute of k_compress done for this context's device
@@ -87,7 +88,8 @@ struct hdlz_ctx {
 };
 
 namespace hdlz {
-constexpr int kHostPipe = 6;   // chunks in flight in the *_host pipelines: deep enough that neither copy direction waits for the host
+constexpr int kHostPipeMax = 6;
+constexpr int kHostPipe = 3;   // streams (= chunks in flight) of the *_host pipelines; more only crowd the copy engines' queues (tools/pcie_pattern.py)
 // Makes the context's device current for one entry point and restores the caller's device on return
 // (an engine on GPU k must not change the calling thread's current device).
 struct DeviceGuard {
