@@ -303,6 +303,10 @@ class Engine(object):
         """A CompressStream on this engine."""
         return CompressStream(self)
 
+    def decompress_stream(self, max_out=1 << 20, flags=0):
+        """A DecompressStream on this engine."""
+        return DecompressStream(self, max_out, flags)
+
     def sync(self, stream=0):
         self._check(self._lib.hdlz_stream_sync(self._ctx, stream or None))
 
@@ -342,6 +346,55 @@ class CompressStream(object):
     def close(self):
         if self._st.value:
             self._lib.hdlz_cstream_end(self._st)
+            self._st = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DecompressStream(object):
+    """One decompress stream fed in pieces (hdlz_dstream_*): the reference's decoder running while the host is
+    still writing (deflate.py:1529) and the host reading as o_oprogress advances.  feed() returns the output bytes
+    that became available (at most `room` of them: the rest waits on the device), finish() the rest; joined they
+    equal Engine.decompress() of the whole stream."""
+
+    def __init__(self, engine, max_out=1 << 20, flags=0):
+        self._eng = engine
+        self._lib = engine._lib
+        self._st = ctypes.c_void_p()
+        self.max_out = int(max_out)
+        engine._check(self._lib.hdlz_dstream_begin(engine._ctx, self.max_out, int(flags), ctypes.byref(self._st)))
+        self.in_progress = 0           # input byte position the decoder has reached (o_iprogress)
+
+    def feed(self, data, room=None):
+        data = bytes(data)
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
+        cap = self.max_out if room is None else int(room)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        n, prog = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._eng._check(self._lib.hdlz_dstream_feed(self._st, src.ctypes.data, len(data), out.ctypes.data, cap,
+                                                     ctypes.byref(n), ctypes.byref(prog)))
+        self.in_progress = int(prog.value)
+        return out[:n.value].tobytes()
+
+    def finish(self, room=None):
+        """-> the remaining output (all of it unless `room` is given; then call again while .remaining)."""
+        cap = self.max_out if room is None else int(room)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        n, rem, st = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._eng._check(self._lib.hdlz_dstream_finish(self._st, out.ctypes.data, cap, ctypes.byref(n), ctypes.byref(rem),
+                                                       ctypes.byref(st)))
+        self.remaining = int(rem.value)
+        if st.value:
+            raise StreamError(st.value)
+        return out[:n.value].tobytes()
+
+    def close(self):
+        if self._st.value:
+            self._lib.hdlz_dstream_end(self._st)
             self._st = ctypes.c_void_p()
 
     def __del__(self):

@@ -46,6 +46,10 @@ SIGNATURES = {
     "hdlz_cstream_feed": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "hdlz_cstream_finish": (cint, [vp, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "hdlz_cstream_end": (cint, [vp]),
+    "hdlz_dstream_begin": (cint, [vp, u32, u32, ctypes.POINTER(vp)]),
+    "hdlz_dstream_feed": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
+    "hdlz_dstream_finish": (cint, [vp, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]),
+    "hdlz_dstream_end": (cint, [vp]),
     "hdlz_dev_alloc": (cint, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
     "hdlz_dev_free": (cint, [vp, vp]),
     "hdlz_host_alloc_pinned": (cint, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),

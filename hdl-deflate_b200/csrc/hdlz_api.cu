@@ -696,6 +696,130 @@ int hdlz_cstream_end(hdlz_cstream *st)
     return HDLZ_SUCCESS;
 }
 
+// ---- decompress stream fed in pieces (see include/hdlz.h) -----------------------------------------------
+struct hdlz_dstream {
+    hdlz_ctx *ctx;
+    uint8_t *d_in;            // every byte fed so far
+    size_t in_cap;
+    uint32_t received;
+    uint8_t *d_out;           // the stream's whole output: also the window of the back-references
+    uint32_t out_cap;
+    uint32_t flags;
+    hdlz::InflateCtl *d_ctl;
+    hdlz::InflateCtl h_ctl;   // mirror of the device record after the last launch
+    uint32_t delivered;       // output bytes handed to the caller so far
+    bool final_run;           // the closing launch has run
+};
+
+namespace {
+// runs the decoder over what has arrived and hands the caller up to out_cap of the bytes not yet delivered
+int dstream_run(hdlz_dstream *st, bool final_input, uint8_t *out, uint32_t out_cap, uint32_t *out_len)
+{
+    hdlz_ctx *ctx = st->ctx;
+    cudaStream_t s = ctx->stream;
+    if (!st->h_ctl.done && !st->final_run) {
+        int rc = launch_inflate_stream(ctx, st->d_in, st->received, final_input, st->d_out, st->out_cap, st->flags, st->d_ctl, s);
+        if (rc) return rc;
+        HDLZ_CUDA(cudaMemcpyAsync(&st->h_ctl, st->d_ctl, sizeof(hdlz::InflateCtl), cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaStreamSynchronize(s));
+        if (final_input) st->final_run = true;
+    }
+    const uint32_t have = st->h_ctl.o - st->delivered;
+    const uint32_t n = have < out_cap ? have : out_cap;
+    if (n) {
+        HDLZ_CUDA(cudaMemcpyAsync(out, st->d_out + st->delivered, n, cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaStreamSynchronize(s));
+        st->delivered += n;
+    }
+    *out_len = n;
+    return HDLZ_SUCCESS;
+}
+}  // namespace
+
+int hdlz_dstream_begin(hdlz_ctx *ctx, uint32_t max_out, uint32_t flags, hdlz_dstream **out)
+{
+    HDLZ_ENTER(ctx);
+    if (!out) return set_error(HDLZ_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (max_out >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "max_out does not fit LMAX");
+    hdlz_dstream *st = new hdlz_dstream();
+    memset(st, 0, sizeof *st);
+    st->ctx = ctx;
+    st->out_cap = max_out;
+    st->flags = flags & (HDLZ_F_VERIFY_HEADER | HDLZ_F_VERIFY_ADLER | HDLZ_F_RAW | HDLZ_F_GZIP);
+    st->in_cap = 1u << 16;
+    cudaError_t e = cudaMalloc((void **)&st->d_in, st->in_cap + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_out, (size_t)max_out + 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_ctl, sizeof(hdlz::InflateCtl));
+    if (e == cudaSuccess) e = cudaMemsetAsync(st->d_ctl, 0, sizeof(hdlz::InflateCtl), ctx->stream);
+    if (e != cudaSuccess) {
+        hdlz_dstream_end(st);
+        return cuda_fail(e, "cudaMalloc(stream)");
+    }
+    *out = st;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_dstream_feed(hdlz_dstream *st, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap, uint32_t *out_len,
+                      uint32_t *in_progress)
+{
+    if (!st) return set_error(HDLZ_ERR_INVALID, "null stream");
+    HDLZ_ENTER(st->ctx);
+    if ((!in && len) || !out_len || (!out && out_cap)) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (st->final_run) return set_error(HDLZ_ERR_INVALID, "stream already finished");
+    if ((uint64_t)st->received + len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
+    cudaStream_t s = st->ctx->stream;
+    *out_len = 0;
+    if ((size_t)st->received + len > st->in_cap) {            // grow: the bytes so far move to the new buffer
+        size_t cap = st->in_cap;
+        while (cap < (size_t)st->received + len) cap *= 2;
+        uint8_t *nb = nullptr;
+        HDLZ_CUDA(cudaMalloc((void **)&nb, cap + 16));
+        cudaError_t e = cudaMemcpyAsync(nb, st->d_in, st->received, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            cudaFree(nb);
+            return cuda_fail(e, "stream input move");
+        }
+        cudaFree(st->d_in);
+        st->d_in = nb;
+        st->in_cap = cap;
+    }
+    if (len) HDLZ_CUDA(cudaMemcpyAsync(st->d_in + st->received, in, len, cudaMemcpyHostToDevice, s));
+    st->received += len;
+    rc = dstream_run(st, false, out, out_cap, out_len);      // synchronises: `in` may be reused by the caller
+    if (rc) return rc;
+    if (in_progress) *in_progress = st->h_ctl.started ? (uint32_t)(st->h_ctl.bitpos >> 3) : 0u;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_dstream_finish(hdlz_dstream *st, uint8_t *out, uint32_t out_cap, uint32_t *out_len, uint32_t *remaining,
+                        uint32_t *status)
+{
+    if (!st) return set_error(HDLZ_ERR_INVALID, "null stream");
+    HDLZ_ENTER(st->ctx);
+    if (!out_len || (!out && out_cap)) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    *out_len = 0;
+    rc = dstream_run(st, true, out, out_cap, out_len);
+    if (rc) return rc;
+    if (remaining) *remaining = st->h_ctl.o - st->delivered;
+    if (status) *status = st->h_ctl.status;
+    return HDLZ_SUCCESS;
+}
+
+int hdlz_dstream_end(hdlz_dstream *st)
+{
+    if (!st) return HDLZ_SUCCESS;
+    DeviceGuard guard;
+    guard.enter(st->ctx->device);
+    cudaStreamSynchronize(st->ctx->stream);
+    if (st->d_in) cudaFree(st->d_in);
+    if (st->d_out) cudaFree(st->d_out);
+    if (st->d_ctl) cudaFree(st->d_ctl);
+    delete st;
+    return HDLZ_SUCCESS;
+}
+
 int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr)
 {
     HDLZ_ENTER(ctx);

@@ -122,6 +122,18 @@ struct StreamCtl {
     uint32_t carry, adler_a, adler_b, pw, lbit;
     uint32_t out_words; // 32-bit words this launch wrote (the closing launch reports bytes through out_len)
 };
+// what a decompress stream carries from one launch to the next (device memory; see k_inflate<true>)
+struct InflateCtl {
+    uint32_t started;      // a resume point is recorded
+    uint32_t at_header;    // resume at a block header (bitpos) / inside a Huffman block (tables from hdr_bitpos, then bitpos)
+    uint32_t final_blk;    // BFINAL of the block being decoded
+    uint32_t o;            // output bytes produced so far
+    unsigned long long bitpos, hdr_bitpos;
+    uint32_t done;         // the stream has ended (status is final)
+    uint32_t status;
+};
+int launch_inflate_stream(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t received, bool final_input, uint8_t *d_out,
+                          uint32_t out_cap, uint32_t flags, InflateCtl *d_ctl, cudaStream_t s);
 int launch_compress_stream(hdlz_ctx *ctx, const uint8_t *d_in_virtual, uint32_t received, uint8_t *d_out, uint32_t *d_out_len,
                            uint32_t *d_status, StreamCtl *d_ctl, unsigned long long *d_queue, cudaStream_t s);
 

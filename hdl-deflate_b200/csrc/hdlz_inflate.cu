@@ -111,6 +111,12 @@ struct Reader {
         acc = (uint64_t)(next_word() >> sh);
         fill = 32 - sh;
     }
+    // position the reader at bit `b` of the stream
+    __device__ __forceinline__ void seek_bits(uint64_t b)
+    {
+        seek((uint32_t)(b >> 3));                // leaves fill >= 8
+        if (b & 7u) drop((uint32_t)(b & 7u));
+    }
     __device__ __forceinline__ void refill()     // call when fill < 32; afterwards fill >= 32
     {
         acc |= (uint64_t)next_word() << fill;
@@ -204,11 +210,24 @@ __device__ __forceinline__ int decode(Reader &r, const Huff &h)
     return -1;
 }
 
+// kStream: ONE stream whose input is still arriving (hdlz_dstream_*).  `received` bytes of it are in `in`; unless
+// `final_input` says these are all, the launch stops where the next step could run out of input — before a block
+// header it cannot see whole, or before a symbol when fewer than 64 bits are left — and records in *ctl what the
+// reference's FSM keeps between clocks: the bit cursor (`di` / `dio`), the output cursor (`do`), where the
+// current block's header started (its tables are rebuilt from there on the next launch) and BFINAL.  The next
+// launch carries on from the record; the output so far stays in `out`, which is also the window.  This is the
+// reference's decompressor waiting at `di >= isize - 4` until more input or IDLE (deflate.py:1529).  Compiled
+// out of the batch kernel.
+constexpr uint32_t kHeaderReserve = 320;     // bytes a dynamic block header can take (17 + 19 * 3 + 316 * 7 bits)
+constexpr uint32_t kSymbolReserve = 64;      // bits: one length / distance pair with its extra bits is at most 48
+
+template <bool kStream>
 __global__ void __launch_bounds__(kWarps * 32)
 k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint64_t in_stride,
           const uint32_t *__restrict__ in_len, uint8_t *out, uint64_t out_stride, uint32_t out_cap,
           uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, uint32_t flags,
-          const uint32_t *__restrict__ work_list, const uint32_t *__restrict__ work_count)
+          const uint32_t *__restrict__ work_list, const uint32_t *__restrict__ work_count, InflateCtl *ctl,
+          uint32_t received, uint32_t final_input)
 {
     // Work items: every stream (work_list == nullptr) or the streams the lane-per-stream kernel
     // handed over (dynamic blocks, unaligned buffers).  Persistent: warps stride over the items.
@@ -239,7 +258,7 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
     const uint64_t sid = work_list ? (uint64_t)work_list[item] : item;
     __syncwarp();
 
-    const uint32_t n_in = in_len[sid];
+    const uint32_t n_in = kStream ? received : in_len[sid];
     const uint8_t *src = in + (in_off ? in_off[sid] : sid * in_stride);
     uint8_t *dst = out + sid * out_stride;
 
@@ -264,13 +283,41 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
     // container: zlib (the reference's, header skipped: di = 2, deflate.py:644), raw deflate or gzip
     const Frame frame = parse_frame(src, n_in, flags);
     st = frame.status;
+    bool suspended = false;          // kStream: this launch stops short of the end of the stream
+    if (kStream && !final_input && st == HDLZ_ST_TRUNCATED) {        // the container header has not arrived yet
+        st = HDLZ_OK;
+        suspended = true;
+    }
 
-    if (st == HDLZ_OK) {
-        r.seek(frame.body);
+    if (st == HDLZ_OK && !suspended) {
         const int64_t limit = 8 * (int64_t)n_in;
         const uint32_t wi_guard = (r.end + 8) / 4 + 2;   // words past the stream end: stop a runaway decode
         uint32_t final_blk = 0;
+        bool in_block = false;       // kStream: resuming inside a Huffman block
+        if (kStream && ctl->started) {
+            o = ctl->o;
+            of = o;
+            in_block = !ctl->at_header;
+            r.seek_bits(in_block ? ctl->hdr_bitpos : ctl->bitpos);
+        } else {
+            r.seek(frame.body);
+        }
+        auto suspend = [&](bool at_header, int64_t bits, int64_t hdr_bits) {
+            suspended = true;
+            if (lane == 0) {
+                ctl->started = 1;
+                ctl->at_header = at_header ? 1u : 0u;
+                ctl->bitpos = (uint64_t)bits;
+                ctl->hdr_bitpos = (uint64_t)hdr_bits;
+                ctl->final_blk = final_blk;
+            }
+        };
         do {
+            const int64_t hdr_bits = r.bitpos();
+            if (kStream && !final_input && hdr_bits + 8 * (int64_t)kHeaderReserve > limit) {
+                suspend(true, hdr_bits, hdr_bits);
+                break;
+            }
             if (r.fill < 32) r.refill();
             final_blk = r.get(1);
             const uint32_t type = r.get(2);
@@ -282,6 +329,10 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
                 const uint32_t len = src[byte] | ((uint32_t)src[byte + 1] << 8);
                 const uint32_t nlen = src[byte + 2] | ((uint32_t)src[byte + 3] << 8);
                 if ((len ^ 0xFFFFu) != nlen) { st = HDLZ_ST_BAD_STORED; break; }
+                if (kStream && !final_input && (uint64_t)byte + 4 + len > n_in) {     // the block's bytes are still arriving
+                    suspend(true, hdr_bits, hdr_bits);
+                    break;
+                }
                 if ((uint64_t)byte + 4 + len > n_in) { st = HDLZ_ST_TRUNCATED; break; }
                 if ((uint64_t)o + len > out_cap) { st = HDLZ_ST_OUT_OVERFLOW; break; }
                 flush_literals();
@@ -348,8 +399,17 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
                 if (build(hd, ll + nlen, (int)ndist, true, ws, lane)) { st = HDLZ_ST_BAD_CODE; break; }
             }
 
+            if (kStream && in_block) {                 // tables rebuilt: back to where the previous launch stopped
+                r.seek_bits(ctl->bitpos);
+                in_block = false;
+            }
             // ---- symbol loop (NEXT / INFLATE / D_NEXT / COPY, deflate.py:1402-1659) ----
             for (;;) {
+                if (kStream && !final_input && r.bitpos() + (int64_t)kSymbolReserve > limit) {
+                    flush_literals();
+                    suspend(false, r.bitpos(), hdr_bits);
+                    break;
+                }
                 if (r.fill < 32) {
                     r.refill();
                     if (r.wi > wi_guard) { st = HDLZ_ST_TRUNCATED; break; }
@@ -385,12 +445,12 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
                 o += len;
                 of = o;
             }
-            if (st != HDLZ_OK) break;
+            if (st != HDLZ_OK || suspended) break;
             if (r.bitpos() > limit) { st = HDLZ_ST_TRUNCATED; break; }
         } while (!final_blk);
 
         flush_literals();
-        if (st == HDLZ_OK) {
+        if (st == HDLZ_OK && !suspended) {
             // the trailer (zlib: Adler-32, four bytes) must exist after the next byte boundary ("NO EOF!",
             // deflate.py:1535-1539)
             const int64_t bp = r.bitpos();
@@ -425,7 +485,14 @@ k_inflate(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, u
         }
     }
 
-    if (lane == 0) {
+    if (kStream) {
+        __syncwarp();
+        if (lane == 0) {
+            ctl->o = o;                          // bytes in `out` so far (all written)
+            ctl->done = suspended ? 0u : 1u;
+            ctl->status = st;
+        }
+    } else if (lane == 0) {
         out_len[sid] = st == HDLZ_OK ? o : 0;
         if (status) status[sid] = st;
     }
@@ -443,8 +510,19 @@ int launch_inflate_general(hdlz_ctx *ctx, const uint8_t *d_in, const uint64_t *d
     uint64_t blocks = (n + kWarps - 1) / kWarps;
     const uint64_t resident = (uint64_t)ctx->sm_count * 5;       // 38 KiB of shared memory per CTA
     if (blocks > resident) blocks = resident;
-    k_inflate<<<(unsigned)blocks, kWarps * 32, 0, s>>>(d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap,
-                                                        d_out_len, d_status, n, flags, work_list, work_count);
+    k_inflate<false><<<(unsigned)blocks, kWarps * 32, 0, s>>>(d_in, d_in_off, in_stride, d_in_len, d_out, out_stride, out_cap,
+                                                               d_out_len, d_status, n, flags, work_list, work_count, nullptr, 0, 0);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
+
+// One launch of the stream kernel (hdlz_dstream_feed / hdlz_dstream_finish, hdlz_api.cu): a single warp works.
+int launch_inflate_stream(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t received, bool final_input, uint8_t *d_out,
+                          uint32_t out_cap, uint32_t flags, InflateCtl *d_ctl, cudaStream_t s)
+{
+    k_inflate<true><<<1, kWarps * 32, 0, s>>>(d_in, nullptr, 0, nullptr, d_out, 0, out_cap, nullptr, nullptr, 1, flags, nullptr,
+                                              nullptr, d_ctl, received, final_input ? 1u : 0u);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;

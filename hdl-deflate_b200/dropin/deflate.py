@@ -109,11 +109,25 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
         st["fed"] += IBSIZE
         st["out"] = st["out"] + st["stream"].feed(piece)
 
+    def feed_dstream():
+        """STARTD with input still arriving (test_deflate.py:136-169): the same for the decoder (hdlz_dstream_feed) —
+        the reference inflates as far as the bytes received allow and waits at `di >= isize - 4` (deflate.py:1529);
+        what it has produced is readable through o_oprogress."""
+        eng = _get_backend()
+        if st["stream"] is None:
+            if not hasattr(eng, "decompress_stream"):
+                return
+            st["stream"] = eng.decompress_stream((1 << LMAX) - 1)
+            st["out"] = b""
+        piece = bytes(lin[st["fed"]:st["fed"] + IBSIZE])
+        st["fed"] += IBSIZE
+        st["out"] = st["out"] + st["stream"].feed(piece)
+
     def run_job():
         data = bytes(lin[:st["isize"] + 1])
         eng = _get_backend()
         try:
-            if st["job"] == STARTC and st["stream"] is not None:
+            if st["stream"] is not None:
                 stream, st["stream"] = st["stream"], None
                 try:
                     return st["out"] + stream.feed(data[st["fed"]:]) + stream.finish()
@@ -180,10 +194,12 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
                     o_iprogress.next = isize - slack if isize > slack else 0
                     # bytes written in order since the START, a whole IBSIZE of them beyond what the engine has
                     # (plus its 32-byte look-ahead): hand them over while the host keeps writing
-                    if st["job"] == STARTC and mode == WRITE and int(i_waddr) == isize and \
-                            isize + 1 - st["fed"] >= IBSIZE + 2 * CWINDOW:
+                    if mode == WRITE and int(i_waddr) == isize and isize + 1 - st["fed"] >= IBSIZE + 2 * CWINDOW:
                         try:
-                            feed_stream()
+                            if st["job"] == STARTC:
+                                feed_stream()
+                            else:
+                                feed_dstream()
                         except ValueError as e:
                             raise Error(str(e).split(" (")[0])
                         if st["stream"] is not None:

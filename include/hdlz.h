@@ -230,6 +230,30 @@ int hdlz_cstream_feed(hdlz_cstream *stream, const uint8_t *in, uint32_t len, uin
 int hdlz_cstream_finish(hdlz_cstream *stream, uint8_t *out, uint32_t out_cap, uint32_t *out_len, uint32_t *status);
 int hdlz_cstream_end(hdlz_cstream *stream);
 
+/* The decompressor's counterpart.  The reference inflates while the host is still writing the stream: the FSM
+ * waits at `di >= isize - 4` until more input arrives or the host goes IDLE (deflate.py:1529), its output ring
+ * fills as it goes and the host reads bytes as o_oprogress advances (deflate.py:1531, 1597; test bench
+ * test_deflate.py:136-194).  hdlz_dstream_* is that: feed the stream in pieces of any size; every call decodes
+ * as far as the input received so far allows — the kernel stops before a block header it cannot see whole
+ * (320 bytes) or a symbol with fewer than 64 bits left, records bit cursor, output cursor and the position of
+ * the current block's header on the device, and the next call carries on from there — and hands back up to
+ * out_cap of the output bytes not yet delivered (what does not fit stays on the device: the back-pressure of
+ * the reference's output ring).  The bytes of all calls, joined, are what hdlz_decompress_stream gives for the
+ * whole stream.  `flags` as hdlz_decompress_batch (containers, verification; checksums are checked by the
+ * closing call).
+ *   begin   max_out = capacity for the whole output (< 2^HDLZ_LMAX)
+ *   feed    out <- up to out_cap new output bytes, *out_len their count, *in_progress the input byte position
+ *           the decoder has reached (o_iprogress)
+ *   finish  no more input: decodes to the end.  Delivers up to out_cap bytes; *remaining = bytes still to be
+ *           fetched (call finish again with more room), *status as hdlz_decompress_stream. */
+typedef struct hdlz_dstream hdlz_dstream;
+int hdlz_dstream_begin(hdlz_ctx *ctx, uint32_t max_out, uint32_t flags, hdlz_dstream **stream);
+int hdlz_dstream_feed(hdlz_dstream *stream, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                      uint32_t *out_len, uint32_t *in_progress);
+int hdlz_dstream_finish(hdlz_dstream *stream, uint8_t *out, uint32_t out_cap, uint32_t *out_len, uint32_t *remaining,
+                        uint32_t *status);
+int hdlz_dstream_end(hdlz_dstream *stream);
+
 /* ---- device memory helpers (for hosts without their own CUDA allocator) --- */
 int hdlz_dev_alloc(hdlz_ctx *ctx, size_t bytes, void **d_ptr);
 int hdlz_dev_free(hdlz_ctx *ctx, void *d_ptr);

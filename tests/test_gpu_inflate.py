@@ -361,3 +361,86 @@ def test_two_phase_route_shapes(engine):
     assert (status == 9).all()
     _, _, status = engine.decompress_host(bad, blens, len(plains[4]) - 1, flags=0)
     assert (status == 6).all()
+
+
+def test_decompress_stream_fed_in_pieces(engine):
+    """hdlz_dstream_*: a stream fed in pieces inflates as far as the input received allows (the reference's decoder
+    waiting at `di >= isize - 4`, deflate.py:1529) and the pieces of output, joined, equal the one-shot result:
+    the state kept on the device between calls (bit cursor, output cursor, header position of the current block)
+    survives any cut — inside a dynamic block header, a stored block, a symbol."""
+    import gzip
+    rnd = random.Random(99)
+    text = b"".join(b"line %d: %s\n" % (i, bytes(rnd.choice(b"abcdefghij ") for _ in range(rnd.randrange(10, 60))))
+                    for i in range(6000))                       # ~260 kB, several dynamic blocks at level 6
+    noise = bytes(rnd.randrange(256) for _ in range(70000))      # stored blocks
+    co = zlib.compressobj(6)
+    mixed = co.compress(text[:50000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(noise[:30000]) + \
+        co.flush(zlib.Z_SYNC_FLUSH) + co.compress(text[50000:90000]) + co.flush()
+    cases = [
+        (zlib.compress(text, 6), text, 0),
+        (zlib.compress(text, 9), text, hz.F_VERIFY_ADLER),
+        (zlib.compress(noise, 0), noise, hz.F_VERIFY_ADLER),
+        (mixed, text[:50000] + noise[:30000] + text[50000:90000], hz.F_VERIFY_ADLER),
+        (engine.compress(text[:100000]), text[:100000], hz.F_VERIFY_ADLER),            # the reference's fixed-block format
+        (gzip.compress(text[:80000], 6), text[:80000], hz.F_GZIP | hz.F_VERIFY_ADLER),
+        (zlib.compress(b"", 6), b"", hz.F_VERIFY_ADLER),
+        (zlib.compress(b"abc", 6), b"abc", 0),
+    ]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    cases.append((co.compress(text[:60000]) + co.flush(), text[:60000], hz.F_RAW))
+    for ci, (stream, plain, flags) in enumerate(cases):
+        for sizes in ([1], [7, 100, 3], [2048], [1, 2, 7, 33, 100, 1024, 1100, 4096, 20000], [len(stream) + 1]):
+            if sizes == [1] and len(stream) > 3000:
+                continue                                         # byte-wise only for the small streams
+            s = engine.decompress_stream(max_out=len(plain) + 64, flags=flags)
+            got, pos, progress = bytearray(), 0, 0
+            while pos < len(stream):
+                n = rnd.choice(sizes)
+                got += s.feed(stream[pos:pos + n])
+                pos += n
+                assert progress <= s.in_progress <= pos          # o_iprogress never runs ahead of the input
+                progress = s.in_progress
+                assert bytes(got) == plain[:len(got)]            # what has been handed out is final
+            if len(stream) > 20000 and max(sizes) < 5000:
+                assert len(got) > 0.8 * len(plain), (ci, sizes)  # most of the output was out before finish()
+            got += s.finish()
+            s.close()
+            assert bytes(got) == plain, (ci, sizes)
+        assert engine.decompress(stream, flags=flags) == plain
+    # back-pressure: the caller takes 1000 bytes per call, the rest waits on the device
+    stream, plain = cases[0][0], cases[0][1]
+    s = engine.decompress_stream(max_out=len(plain))
+    got = bytearray()
+    for pos in range(0, len(stream), 5000):
+        piece = s.feed(stream[pos:pos + 5000], room=1000)
+        assert len(piece) <= 1000
+        got += piece
+    while True:
+        got += s.finish(room=1000)
+        if not s.remaining:
+            break
+    s.close()
+    assert bytes(got) == plain
+    # errors: a stream cut short, a damaged stream, an output that does not fit
+    s = engine.decompress_stream(max_out=len(plain))
+    s.feed(stream[:len(stream) // 2])
+    with pytest.raises(hz.StreamError) as e:
+        s.finish()
+    assert e.value.status == 5                                   # TRUNCATED ("NO EOF!")
+    s.close()
+    bad = bytearray(stream)
+    bad[-2] ^= 0x55
+    s = engine.decompress_stream(max_out=len(plain), flags=hz.F_VERIFY_ADLER)
+    for pos in range(0, len(bad), 4096):
+        s.feed(bytes(bad[pos:pos + 4096]))
+    with pytest.raises(hz.StreamError) as e:
+        s.finish()
+    assert e.value.status == 9                                   # BAD_ADLER
+    s.close()
+    s = engine.decompress_stream(max_out=1000)
+    with pytest.raises(hz.StreamError) as e:
+        for pos in range(0, len(stream), 4096):
+            s.feed(stream[pos:pos + 4096])
+        s.finish()
+    assert e.value.status == 6                                   # OUT_OVERFLOW
+    s.close()
