@@ -748,8 +748,11 @@ k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict_
                 bool ready = false;
                 if (pending) {
                     ready = true;
-                    for (uint32_t b = 0; b < need && ready; b += 32) ready = range_clear(bm, cs + b, min(32u, need - b));
+                    // what lies before this step's output is final; only a source that reaches into the step is checked
+                    if (cs + need > O0)
+                        for (uint32_t b = 0; b < need && ready; b += 32) ready = range_clear(bm, cs + b, min(32u, need - b));
                 }
+                if (__any_sync(HDLZ_FULL_MASK, pending)) {          // a warp with nothing left only keeps the barrier
                 // short copies that do not overlap their source: all their bytes as one list, a byte per lane per pass
                 {
                     const bool flat = ready && len <= 32u && dist >= len;
@@ -807,6 +810,7 @@ k_resolve_tokens(const uint32_t *__restrict__ items, const uint32_t *__restrict_
                     __threadfence_block();                   // a thread still checking this round may already see the bits
                     for (uint32_t b = 0; b < len; b += 32) range_unmark(bm, cd + b, min(32u, len - b));
                     pending = false;
+                }
                 }
                 if (!__syncthreads_or(pending)) break;
             }
