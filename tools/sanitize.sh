@@ -1,10 +1,11 @@
-# compute-sanitizer passes over the GPU parity tests (run through gpurun; a few minutes of box time):
+# compute-sanitizer passes over the GPU parity tests (run through gpurun; several minutes of box time):
 #   memcheck  - out-of-bounds / misaligned accesses of every kernel
 #   racecheck - shared-memory hazards of the warp-synchronous code (the kernels order their shared-memory
 #               phases with __syncwarp only; the two-phase inflater with CTA barriers and a bitmap)
 # Round 2: the selections include the two-phase route (test_two_phase_route_shapes, config4), the window-256
-# kernel, the stream calls and a reduced full-size pass (HDLZ_TEST_FULL_BLOCKS).
+# kernel, the stream calls in both directions, the tree-coded compressor mode and a reduced full-size pass.
 set -x
 SEL='not full_size and not batch_matches_oracle and not randomized and not config3'
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_containers.py tests/test_gpu_inflate.py tests/test_gpu_compress.py -m gpu -x -q -k "$SEL" 2>&1 | tail -6
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_containers.py tests/test_gpu_compress.py tests/test_gpu_inflate.py -m gpu -x -q -k "golden or ragged or same_body or raw_and_gzip or mixed_batch or multi_block or two_phase or window256 or stream_fed or empty_distance" 2>&1 | tail -6
+timeout 1700 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_containers.py tests/test_gpu_inflate.py tests/test_gpu_compress.py tests/test_gpu_tree.py -m gpu -x -q -k "$SEL" 2>&1 | grep -v "Host Frame\|^=========$" | tail -12
+timeout 1700 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_containers.py tests/test_gpu_compress.py tests/test_gpu_inflate.py tests/test_gpu_tree.py -m gpu -x -q -k "golden or ragged or same_body or raw_and_gzip or mixed_batch or multi_block or two_phase or window256 or stream_fed or empty_distance or train_equals or application_tree or long_stream" > gpurun_out/racecheck_full.txt 2>&1
+grep "Race reported\|Error:\|passed\|failed\|SUMMARY" gpurun_out/racecheck_full.txt | sed "s/(const [^)]*)//g" | sort | uniq -c | sort -rn | head -40
