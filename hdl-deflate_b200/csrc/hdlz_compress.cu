@@ -1,4 +1,4 @@
-// hdlz_compress.cu — static-tree deflate compressor, bit-exact with the reference's
+// hdlz_compress.cu — deflate compressor, in its fixed-tree mode bit-exact with the reference's
 // FAST + MATCH10 / CWINDOW=32 engine (deflate.py states CSTATIC, SEARCH, SEARCHF,
 // DISTANCE, CHECKSUM; :734-1016), re-designed for sm_100a.  Not a port of the FSM:
 //
@@ -39,6 +39,11 @@
 //            last tile appends EOB, pad and Adler-32 (deflate.py:771-814).
 //
 // Algorithmic HBM traffic per stream: L bytes read + C bytes written (C = stream size).
+//
+// Two more instantiations share everything up to the parse (so the tokens stay the reference's) and differ in
+// what P3 does with a token (hdlz_tree.cu): kModeTree codes it with the tree of the context
+// instead of the fixed one — one BTYPE = 10 block per stream, opened by a description of the code that is the
+// same bit string for every stream; kModeHist only counts the symbols (hdlz_train_tree).
 
 #include "hdlz_common.cuh"
 

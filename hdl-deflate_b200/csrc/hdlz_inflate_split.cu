@@ -6,10 +6,14 @@
 //   phase 1  k_decode_tokens   one THREAD per stream, decode only.  Symbol decode is serial per stream, so
 //            the batch parallelism is across streams; with no window access in this phase a lane never
 //            waits for a far back-reference, and its tables are small enough to live in shared memory:
-//            an 8-bit literal/length and a 7-bit distance primary table plus the two count arrays of the
-//            canonical code (832 B per lane, interleaved by lane: a bank serves two lanes).
-//            Longer codes (under 1 % of the symbols of level-6 streams) take a canonical bit-serial
-//            decode that resumes after the table's bits.  Output: a compact token stream in global
+//            an 8-bit literal/length table of 16-bit entries and a 7-bit distance table of 8-bit entries
+//            (640 B per lane, interleaved by lane: a bank serves two / four lanes; the counts of the longer
+//            codes ride in two 64-bit registers): ten warps per SM.  Longer codes (2 % of the symbols of
+//            level-6 streams, but some lane of a warp meets one in every second trip) take a canonical
+//            bit-serial search in registers that resumes after the table's bits; the sorted-symbols word it
+//            ends in is asked for with cp.async and taken one trip later.  A lane keeps four input words of
+//            look-ahead; a trip never moves that window and ends in ONE refill from a four-vector cp.async
+//            ring — the same instructions for every lane.  Output: a compact token stream in global
 //            memory — literal bytes, and one 32-bit token per copy
 //                bits 0..7 literals before the copy | 8..16 copy length (0 = none) | 17..31 distance - 1.
 //   phase 2  k_resolve_tokens  one CTA of eight warps per stream, the stream's whole output (<= 32 KiB)
@@ -17,7 +21,9 @@
 //            scan gives every token its literal source and its output position; the threads place their
 //            literals, then their copies in rounds — a bit per output byte says whether it is final, and a
 //            copy runs in the first round in which all it reads is (level-6 copies reach far back: mostly
-//            the first); copies longer than 32 bytes are done by a whole warp.  The finished window goes
+//            the first; a source that lies before the step's output is final without a look at the bits);
+//            a CTA barrier separates a round's readiness checks from its copies and the rounds from each
+//            other; copies longer than 32 bytes are done by a whole warp.  The finished window goes
 //            to HBM with coalesced 128-bit stores, and the optional Adler-32 is taken from the same reads.
 //
 // Algorithmic HBM traffic per stream: C bytes read + L bytes written; the token stream adds its

@@ -97,8 +97,9 @@ def deflate(i_mode, o_done, i_data, o_iprogress, o_oprogress, o_byte,
         far become readable: o_oprogress follows the engine's real output, as it does in the reference."""
         eng = _get_backend()
         if st["stream"] is None:
-            if not fast or not hasattr(eng, "compress_stream") or getattr(eng, "container", 0) == 2:
-                return
+            if not fast or not hasattr(eng, "compress_stream") or getattr(eng, "container", 0) == 2 or \
+                    getattr(eng, "tree", None) is not None:
+                return                     # these jobs run in one piece when the host goes IDLE
             if hasattr(eng, "match10"):
                 eng.match10 = match10
             if hasattr(eng, "fast"):
