@@ -69,6 +69,14 @@ static inline uint64_t host_chunk(uint64_t n, uint64_t bytes_per_item)
     return c < n ? c : n;
 }
 
+// the long-stream compress kernel codes with the fixed tree, the FAST window and the zlib / raw containers
+// (HDLZ_NO_LONG: A/B runs of tools/ and tests/)
+static inline bool long_stream_ok(const hdlz_ctx *ctx, uint32_t len)
+{
+    return len >= HDLZ_LONG_STREAM && !ctx->tree_set && ctx->window == HDLZ_CWINDOW && ctx->container != HDLZ_CONTAINER_GZIP &&
+           !getenv("HDLZ_NO_LONG");
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int check_ctx(hdlz_ctx *ctx, DeviceGuard &guard)
@@ -203,6 +211,7 @@ int hdlz_destroy(hdlz_ctx *c)
     if (c->h_dyn_seen) cudaFreeHost(c->h_dyn_seen);
     if (c->d_queue) cudaFree(c->d_queue);
     if (c->d_tree) cudaFree(c->d_tree);
+    if (c->d_long) cudaFree(c->d_long);
     if (c->d_pack) cudaFree(c->d_pack);
     for (int i = 0; i < 3; i++)
         if (c->d_lane[i]) cudaFree(c->d_lane[i]);
@@ -255,6 +264,10 @@ int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, 
         return set_error(HDLZ_ERR_INVALID, "d_in/d_out must be 16-byte aligned and strides multiples of 16");
     if (!d_in_len && (uniform_len > in_stride || uniform_len >= (1u << HDLZ_LMAX)))
         return set_error(HDLZ_ERR_INVALID, "uniform_len %u does not fit in_stride / LMAX", uniform_len);
+    // a batch of ONE long stream: spread over the whole grid instead of one warp (same bytes)
+    if (n == 1 && !d_in_len && long_stream_ok(ctx, uniform_len) && compress_bound(uniform_len, ctx->container) <= out_stride)
+        return launch_compress_long(ctx, d_in, uniform_len, d_out, compress_bound(uniform_len, ctx->container), d_out_len,
+                                    d_status, (cudaStream_t)stream);
     return launch_compress(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n,
                            (cudaStream_t)stream);
 }
@@ -495,6 +508,7 @@ int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t
     if ((rc = grow((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * sizeof(uint32_t)))) return rc;
     cudaStream_t s = ctx->stream;
     HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, len, cudaMemcpyHostToDevice, s));
+    // (a stream of HDLZ_LONG_STREAM bytes or more goes over the whole grid instead of one warp: hdlz_compress_batch)
     rc = hdlz_compress_batch(ctx, ctx->d_in, in_slot ? in_slot : 16, nullptr, len, ctx->d_out, out_slot, ctx->d_meta + 1,
                              ctx->d_meta + 2, 1, s);
     if (rc) return rc;

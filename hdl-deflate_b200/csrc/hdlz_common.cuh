@@ -42,6 +42,9 @@ struct hdlz_ctx {
     bool wide_attr_set;
     bool stream_attr_set;
     bool tree_attr_set;
+    bool long_attr_set;
+    void *d_long;          // look-back arrays of the long-stream compress kernel (one entry per tile)
+    size_t d_long_cap;
     // application / trained code (hdlz_set_tree, hdlz_train_tree); tree_set false = the reference's fixed code
     bool tree_set;
     uint32_t tree_container;   // container the prefix of `tree` was built for
@@ -151,6 +154,8 @@ int cuda_fail(cudaError_t e, const char *what);
 int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                     uint32_t uniform_len, uint8_t *d_out, uint64_t out_stride, uint32_t *d_out_len,
                     uint32_t *d_status, uint64_t n, cudaStream_t s);
+int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t len, uint8_t *d_out, uint64_t out_bytes,
+                         uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s);
 int launch_compress_hist(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len, uint32_t uniform_len,
                          uint64_t n, unsigned long long *d_hist, cudaStream_t s);
 int refresh_tree(hdlz_ctx *ctx);

@@ -155,13 +155,37 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 // kMode: kModeFixed = the reference's fixed code; kModeTree = the code of *tree (hdlz_set_tree / hdlz_train_tree): same
 // parse, every stream starts with tree->prefix, tokens come from tree->lut; kModeHist = no output, the symbols the
 // parse produces are counted into hist[] (hdlz_train_tree).
-template <int kMaxMatch, bool kStream, int kMode>
+// kLong: ONE long stream (`uniform_len` bytes at `in`) spread over the whole grid, a tile of 1024 positions per
+// warp at a time, tiles handed out in order by the queue head.  What the reference's FSM carries from position to
+// position crosses tile borders through `lbuf` (three arrays of one entry per tile, zeroed by the launcher):
+//   - the parse (`di += match`, deflate.py:960): a tile publishes its MAP carry-in -> carry-out (ten nibbles; the
+//     greedy parse forgets where it started within a few tokens, so the map is almost always constant and the
+//     carry-out known at once) and finds its own carry-in by looking back over the maps of its predecessors;
+//   - the bit cursor (`do` / `doo`, deflate.py:535-567): a decoupled look-back over the tiles' bit counts gives a
+//     tile its place in the stream; the tile's words go straight there, the two words it shares with its
+//     neighbours by atomic OR into the zeroed output;
+//   - the Adler-32 sums (deflate.py:826-831): per tile, folded together by the last tile (adler32_combine rule).
+// The bytes are those of the one-warp kernel (tests/test_gpu_compress.py::test_long_stream_over_the_grid).
+constexpr unsigned long long kLbResolved = 2ull << 62, kLbPartial = 1ull << 62, kLbValue = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long lb_poll(const unsigned long long *p)     // spin until the entry is published
+{
+    unsigned long long v;
+    do {
+        v = *reinterpret_cast<const volatile unsigned long long *>(p);
+    } while (v == 0ull);
+    return v;
+}
+
+template <int kMaxMatch, bool kStream, int kMode, bool kLong = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *__restrict__ in_len,
            uint32_t uniform_len, uint8_t *__restrict__ out, uint64_t out_stride,
            uint32_t *__restrict__ out_len, uint32_t *__restrict__ status, uint64_t n_streams, unsigned long long *queue,
-           uint32_t container, StreamCtl *ctl, const TreeDev *__restrict__ tree, unsigned long long *hist)
+           uint32_t container, StreamCtl *ctl, const TreeDev *__restrict__ tree, unsigned long long *hist,
+           unsigned long long *lbuf = nullptr)
 {
+    static_assert(!kLong || (!kStream && kMode == kModeFixed), "the long-stream mode codes with the fixed tree");
     extern __shared__ uint4 smem_raw[];
     uint32_t *LT = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *DC = LT + 256;
@@ -194,19 +218,30 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
     // Work distribution: every warp starts on stream <its global index>, later streams come from a
     // device-wide queue head (one atomic per stream).  A static stride would leave the SM idle
     // wherever a CTA of the grid was not resident from the start and ran after the others.
-    const uint64_t n_warps = (uint64_t)gridDim.x * kWarpsPerCta;
-    for (uint64_t sid = (uint64_t)blockIdx.x * kWarpsPerCta + warp; sid < n_streams;) {
+    const uint64_t n_warps = kLong ? 0ull : (uint64_t)gridDim.x * kWarpsPerCta;
+    // kLong: `sid` is a TILE of the one stream and every tile comes from the queue head, the first one too: a tile
+    // may wait for its predecessors, so they must belong to warps that already run
+    const uint64_t n_tiles = kLong ? ((uint64_t)uniform_len + kTile - 1) / kTile : 0ull;
+    unsigned long long *lb_map = lbuf, *lb_bits = lbuf + n_tiles;
+    uint32_t *lb_adler = reinterpret_cast<uint32_t *>(lbuf + 2 * n_tiles);
+    uint64_t sid0 = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
+    if constexpr (kLong) {
+        unsigned long long tk0 = 0;
+        if (lane == 0) tk0 = atomicAdd(queue, 1ull);
+        sid0 = __shfl_sync(HDLZ_FULL_MASK, tk0, 0);
+    }
+    for (uint64_t sid = sid0; sid < (kLong ? n_tiles : n_streams);) {
         unsigned long long next_ticket = 0;
         if (lane == 0) next_ticket = atomicAdd(queue, 1ull);           // in flight while this stream is processed
-        const uint32_t L = in_len ? in_len[sid] : uniform_len;
-        const uint8_t *src = in + sid * in_stride;
-        uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + sid * out_stride);
+        const uint32_t L = kLong ? uniform_len : in_len ? in_len[sid] : uniform_len;
+        const uint8_t *src = kLong ? in : in + sid * in_stride;
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(kLong ? out : out + sid * out_stride);
         uint64_t need = 0;               // slot size this stream may need
         if constexpr (kMode == kModeFixed) need = compress_bound(L, container);
         else if constexpr (kMode == kModeTree)
             need = ((((uint64_t)tree->prefix_bits + (uint64_t)L * tree->worst_bits + (tree->eob >> 16) + 7) >> 3) +
                     (container == HDLZ_CONTAINER_GZIP ? 8u : container == HDLZ_CONTAINER_RAW ? 0u : 4u) + 15) & ~15ull;
-        if (!kStream && (L < HDLZ_MIN_INPUT || need > out_stride)) {
+        if (!kStream && !kLong && (L < HDLZ_MIN_INPUT || need > out_stride)) {
             if (lane == 0 && kMode != kModeHist) {
                 out_len[sid] = 0;
                 if (status) status[sid] = L < HDLZ_MIN_INPUT ? HDLZ_ST_SHORT_INPUT : HDLZ_ST_OUT_OVERFLOW;
@@ -246,6 +281,10 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 
         uint32_t t_first = 0, t_stop = L;
         bool closing = true;             // this launch reaches the end of the stream
+        if constexpr (kLong) {           // exactly the tile `sid`
+            t_first = (uint32_t)sid * kTile;
+            t_stop = t_first + kTile < L ? t_first + kTile : L;
+        }
         if (kStream) {
             t_first = ctl->t0;
             closing = ctl->final != 0;
@@ -409,6 +448,52 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 unsigned long long *Hs = reinterpret_cast<unsigned long long *>(ws.stage);    // input bytes are dead
                 Hs[lane] = H;
                 __syncwarp();
+                if constexpr (kLong) {
+                    // the tile's map carry-in -> carry-out: lanes 0..9 walk the segments, each from its own carry-in
+                    uint32_t mc = lane < 10 ? (uint32_t)lane : 0u;
+#pragma unroll 8
+                    for (int s = 0; s < 32; ++s) mc = (uint32_t)(Hs[s] >> (4 * mc)) & 15u;
+                    const uint32_t m_lo = __reduce_or_sync(HDLZ_FULL_MASK, lane < 8 ? mc << (4 * lane) : 0u);
+                    const uint32_t m_hi = __reduce_or_sync(HDLZ_FULL_MASK, (lane == 8 || lane == 9) ? mc << (4 * (lane - 8)) : 0u);
+                    const unsigned long long M = (unsigned long long)m_lo | ((unsigned long long)m_hi << 32);
+                    const uint32_t c0 = __shfl_sync(HDLZ_FULL_MASK, mc, 0);
+                    const bool constant = __all_sync(HDLZ_FULL_MASK, lane >= 10 || mc == c0);
+                    uint32_t cin = 0;
+                    if (lane == 0) {
+                        const bool known = sid == 0 || constant;      // the carry-out does not depend on what comes in
+                        if (known) atomicExch(&lb_map[sid], kLbResolved | c0);
+                        else atomicExch(&lb_map[sid], kLbPartial | M);
+                        if (sid != 0) {
+                            // look back: compose the maps of the predecessors until one of them knows its carry-out
+                            // (or the composition has become constant)
+                            unsigned long long comp = 0x9876543210ull;     // identity
+                            for (uint64_t j = sid - 1;; --j) {
+                                const unsigned long long v = lb_poll(&lb_map[j]);
+                                if ((v & kLbResolved) != 0ull) {
+                                    cin = (uint32_t)(comp >> (4 * (v & 15ull))) & 15u;
+                                    break;
+                                }
+                                unsigned long long nc = 0;                 // comp after M_j: e -> comp(M_j(e))
+                                bool same = true;
+                                for (int e = 0; e < 10; ++e) {
+                                    const uint32_t x = (uint32_t)(comp >> (4 * ((v >> (4 * e)) & 15ull))) & 15u;
+                                    nc |= (unsigned long long)x << (4 * e);
+                                    same = same && x == (uint32_t)(nc & 15ull);
+                                }
+                                comp = nc;
+                                if (same) {
+                                    cin = (uint32_t)(comp & 15ull);
+                                    break;
+                                }
+                            }
+                            if (!known) {
+                                __threadfence();
+                                atomicExch(&lb_map[sid], kLbResolved | ((M >> (4 * cin)) & 15ull));
+                            }
+                        }
+                    }
+                    carry = __shfl_sync(HDLZ_FULL_MASK, cin, 0);
+                }
                 uint32_t cur = carry;
 #pragma unroll 8
                 for (int s = 0; s < 32; ++s) {
@@ -500,6 +585,39 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 if (lane >= d) incl += o;
             }
             const uint32_t tile_bits = __shfl_sync(HDLZ_FULL_MASK, incl, 31);
+            if constexpr (kLong) {
+                // the tile's place in the stream: bits of all earlier tiles (after the header bits of tile 0)
+                unsigned long long b0 = 0;
+                if (lane == 0) {
+                    lb_adler[sid] = adler_a | (adler_b << 16);      // this tile's own sums (from a = 1, b = 0)
+                    __threadfence();
+                    if (sid == 0) atomicExch(&lb_bits[0], kLbResolved | (unsigned long long)(lbit + tile_bits));
+                    else atomicExch(&lb_bits[sid], kLbPartial | (unsigned long long)tile_bits);
+                }
+                if (sid != 0) {
+                    // look back 32 tiles at a time (lane l reads tile end - 1 - l): bit counts are added up to and
+                    // including the nearest tile that already knows where it ends.  A whole wave of tiles computes
+                    // at once, so a one-entry-at-a-time walk would be thousands of dependent reads long.
+                    for (uint64_t end = sid;; end -= 32) {
+                        const bool in_range = end > (uint64_t)lane;
+                        const unsigned long long v = in_range ? lb_poll(&lb_bits[end - 1 - lane]) : 0ull;
+                        const uint32_t res = __ballot_sync(HDLZ_FULL_MASK, in_range && (v & kLbResolved) != 0ull);
+                        const int stop = res ? __ffs(res) - 1 : 31;
+                        unsigned long long x = (in_range && lane <= stop) ? (v & kLbValue) : 0ull;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(HDLZ_FULL_MASK, x, d);
+                        b0 += x;
+                        if (res) break;                               // tile 0 is always resolved: the walk ends there at the latest
+                    }
+                    if (lane == 0) {
+                        __threadfence();
+                        atomicExch(&lb_bits[sid], kLbResolved | (b0 + tile_bits));
+                    }
+                    pw = 0;
+                    lbit = (uint32_t)(b0 & 31ull);
+                    wbase = (uint32_t)(b0 >> 5);
+                }
+            }
 
             // the tokens are dead: their array becomes the tile's part of the output stream
             __syncwarp();
@@ -531,7 +649,16 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 
             // ---------------- flush ---------------------------------------------------------------------
             uint32_t total = lbit + tile_bits;
-            if (!last_tile) {
+            if (kLong && !last_tile) {
+                // whole words of the tile are its own; the first (if it starts inside one) and the last partial
+                // word are shared with the neighbouring tiles: OR into the zeroed output
+                const uint32_t nfull = total >> 5;
+                for (uint32_t k = lane; k < nfull; k += 32) {
+                    if (k == 0 && lbit != 0) atomicOr(&dst32[wbase], outw[0]);
+                    else dst32[wbase + k] = outw[k];
+                }
+                if (lane == 0 && (total & 31u) != 0u) atomicOr(&dst32[wbase + nfull], outw[nfull]);
+            } else if (!last_tile) {
                 const uint32_t nfull = total >> 5;
                 for (uint32_t k = lane; k < nfull; k += 32) dst32[wbase + k] = outw[k];
                 pw = outw[nfull];
@@ -552,6 +679,32 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
                 const uint32_t nbytes = (total + 7) >> 3;     // pad to a byte (deflate.py:784-787)
                 uint32_t trailer = 4;
+                if constexpr (kLong) {
+                    // Adler-32 of the whole stream from the tiles' sums: (a1, b1, n1) then (a2, b2, n2) give
+                    // a = a1 + a2 - 1, b = b1 + b2 + n2 (a1 - 1)  (mod 65521).  Every earlier tile is full.
+                    // Each lane folds a run of tiles, lane 0 then folds the 32 runs and this tile.
+                    const uint64_t per = (sid + 31) / 32;
+                    const uint64_t j0 = per * lane < sid ? per * lane : sid, j1 = j0 + per < sid ? j0 + per : sid;
+                    uint32_t ra = 1, rb = 0;                       // 32-bit: b + b2 + 1024 * 65520 < 2^27
+                    unsigned long long rn = 0;
+                    for (uint64_t j = j0; j < j1; ++j) {
+                        const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(&lb_adler[j]);
+                        const uint32_t a2 = v & 0xFFFFu, b2 = v >> 16;
+                        rb = (rb + b2 + (uint32_t)kTile * ((ra + 65520u) % 65521u)) % 65521u;
+                        ra = (ra + a2 + 65520u) % 65521u;
+                        rn += kTile;
+                    }
+                    unsigned long long fa = 1, fb = 0;
+                    for (int l = 0; l < 32; ++l) {
+                        const unsigned long long a2 = __shfl_sync(HDLZ_FULL_MASK, ra, l), b2 = __shfl_sync(HDLZ_FULL_MASK, rb, l);
+                        const unsigned long long n2 = __shfl_sync(HDLZ_FULL_MASK, rn, l);
+                        fb = (fb + b2 + (n2 % 65521ull) * (fa + 65520ull)) % 65521ull;
+                        fa = (fa + a2 + 65520ull) % 65521ull;
+                    }
+                    const unsigned long long ta = adler_a, tb = adler_b;         // this tile's own
+                    adler_b = (uint32_t)((fb + tb + (unsigned long long)(n_tile % 65521u) * (fa + 65520ull)) % 65521ull);
+                    adler_a = (uint32_t)((fa + ta + 65520ull) % 65521ull);
+                }
                 if (lane == 0) {
                     uint8_t *ob = reinterpret_cast<uint8_t *>(outw);
                     if (container == HDLZ_CONTAINER_ZLIB) {
@@ -571,11 +724,14 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 else if (container == HDLZ_CONTAINER_GZIP) trailer = 8;
                 __syncwarp();
                 const uint32_t nwords = (nbytes + trailer + 3) >> 2;
-                for (uint32_t k = lane; k < nwords; k += 32) dst32[wbase + k] = outw[k];
+                for (uint32_t k = lane; k < nwords; k += 32) {
+                    if (kLong && k == 0 && lbit != 0) atomicOr(&dst32[wbase], outw[0]);      // shared with the tile before
+                    else dst32[wbase + k] = outw[k];
+                }
                 const bool no_code = kMode == kModeTree && __any_sync(HDLZ_FULL_MASK, uncoded != 0u);
                 if (lane == 0) {
-                    out_len[sid] = no_code ? 0u : 4 * wbase + nbytes + trailer;
-                    if (status) status[sid] = no_code ? HDLZ_ST_NO_CODE : HDLZ_OK;
+                    out_len[kLong ? 0 : sid] = no_code ? 0u : 4 * wbase + nbytes + trailer;
+                    if (status) status[kLong ? 0 : sid] = no_code ? HDLZ_ST_NO_CODE : HDLZ_OK;
                 }
             }
         }
@@ -668,6 +824,41 @@ static int launch_mode(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, c
         k_compress<10, false, kMode><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kMode>(), s>>>(
             d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr,
             ctx->d_tree, d_hist);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
+
+// One long stream over the whole grid (k_compress<.., kLong = true>): hdlz_compress_stream for inputs of many
+// tiles.  d_out must hold compress_bound(len) bytes; it is zeroed here (tiles OR their border words into it).
+int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t len, uint8_t *d_out, uint64_t out_bytes,
+                         uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s)
+{
+    if (!ctx->long_attr_set) {
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->long_attr_set = true;
+    }
+    const uint64_t n_tiles = ((uint64_t)len + kTile - 1) / kTile;
+    const size_t lb_bytes = n_tiles * (2 * sizeof(unsigned long long) + sizeof(uint32_t)) + 16;
+    int rc = grow_device((void **)&ctx->d_long, &ctx->d_long_cap, lb_bytes);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaMemsetAsync(ctx->d_long, 0, lb_bytes, s));
+    HDLZ_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, s));
+    unsigned long long *queue = nullptr;
+    if ((rc = next_queue(ctx, &queue, s))) return rc;
+    uint64_t blocks = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;
+    if (blocks > resident) blocks = resident;
+    unsigned long long *lbuf = reinterpret_cast<unsigned long long *>(ctx->d_long);
+    if (ctx->max_match == 5)
+        k_compress<5, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
+            d_in, 0, nullptr, len, d_out, 0, d_out_len, d_status, 1, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
+    else
+        k_compress<10, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
+            d_in, 0, nullptr, len, d_out, 0, d_out_len, d_status, 1, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;

@@ -45,6 +45,7 @@ extern "C" {
 #define HDLZ_MIN_INPUT 5     /* engine idles while isize < 4 (deflate.py:429-432)    */
 #define HDLZ_OBSIZE 32768    /* decompress window, "ALL valid streams" (README:20-21) */
 #define HDLZ_LMAX 24         /* width of progress / address counters (deflate.py:73-76) */
+#define HDLZ_LONG_STREAM 65536 /* hdlz_compress_stream: from this length on the stream is spread over the whole GPU */
 
 typedef enum hdlz_error {
     HDLZ_SUCCESS = 0,
@@ -204,7 +205,11 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
                               uint32_t *out_len, uint32_t *status, uint64_t n_blocks, uint64_t *out_total);
 
 /* One stream of any length < 2^24 (LMAX): exactly what one STARTC / STARTD job of the
- * port protocol does.  `status` receives the hdlz_status. */
+ * port protocol does.  `status` receives the hdlz_status.  A compress stream of HDLZ_LONG_STREAM bytes or
+ * more is spread over the whole GPU, a tile of 1024 positions per warp (fixed tree, FAST, zlib / raw
+ * container; otherwise one warp works through it): the parse position, the bit cursor and the Adler sums —
+ * what the reference's FSM carries from byte to byte — cross the tile borders by look-back between the
+ * warps, and the bytes are the same. */
 int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
                          uint32_t *out_len, uint32_t *status);
 int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,

@@ -368,3 +368,40 @@ def test_stream_fed_in_pieces(engine):
     finally:
         engine.match10 = True
         engine.container = hz.CONTAINER_ZLIB
+
+
+def test_long_stream_over_the_grid(engine):
+    """hdlz_compress_stream spreads a stream of >= 64 KiB over the whole GPU (k_compress<.., kLong>): tiles are
+    handed out in order, the parse carry crosses tile borders as a composition of per-tile maps, the bit cursor by a
+    decoupled look-back, the Adler sums by the combine rule.  Same bytes as the one-warp kernel and the oracle —
+    including data whose parse never forgets where it started (runs, short periods: the maps are not constant and
+    the look-back has to walk), both MATCH10 settings and the raw container."""
+    rnd = random.Random(77)
+    mixed = b"".join(workload.blocks(4000, 700, 2048))
+    cases = [
+        mixed[:65536], mixed[:65537], mixed[:100000], mixed[:1024 * 1024 + 17], mixed,
+        bytes(300000),                                                   # one run: every token a 10-byte match
+        (b"abcdefg" * 60000)[:400001],                                   # period 7
+        (b"0123456789" * 30000)[:262144 + 5],                            # period 10 = the longest match
+        bytes(rnd.randrange(256) for _ in range(200000)),                # literals only
+        b"".join(bytes([rnd.randrange(4)]) * rnd.randrange(1, 40) for _ in range(20000)),
+    ]
+    for i, data in enumerate(cases):
+        st, want = hdlz_oracle.compress(data)
+        got = engine.compress(data)
+        assert st == 0 and got == want, (i, len(data), len(got), len(want))
+    assert zlib.decompress(engine.compress(cases[4])) == cases[4]
+    engine.match10 = False
+    engine.container = hz.CONTAINER_RAW
+    try:
+        for data in (cases[2], cases[5], cases[6]):
+            assert engine.compress(data) == hdlz_oracle.compress(data, maxlen=5)[1][2:-4]
+    finally:
+        engine.match10 = True
+        engine.container = hz.CONTAINER_ZLIB
+    # the one-warp kernel on the same stream: the same bytes
+    os.environ["HDLZ_NO_LONG"] = "1"
+    try:
+        assert engine.compress(cases[3]) == hdlz_oracle.compress(cases[3])[1]
+    finally:
+        del os.environ["HDLZ_NO_LONG"]
