@@ -391,6 +391,26 @@ def test_long_stream_over_the_grid(engine):
         got = engine.compress(data)
         assert st == 0 and got == want, (i, len(data), len(got), len(want))
     assert zlib.decompress(engine.compress(cases[4])) == cases[4]
+    # random lengths and data mixes: tile borders fall anywhere in runs, matches and literal stretches
+    for trial in range(24):
+        n = rnd.randrange(65536, 700000)
+        parts, have = [], 0
+        while have < n:
+            kind = rnd.randrange(4)
+            m = rnd.randrange(1, 5000)
+            if kind == 0:
+                piece = bytes([rnd.randrange(256)]) * m
+            elif kind == 1:
+                unit = bytes(rnd.randrange(256) for _ in range(rnd.randrange(2, 13)))
+                piece = (unit * (m // len(unit) + 1))[:m]
+            elif kind == 2:
+                piece = bytes(rnd.randrange(256) for _ in range(m))
+            else:
+                piece = workload.block(rnd.randrange(1 << 20), 2048)[:m]
+            parts.append(piece)
+            have += len(piece)
+        data = b"".join(parts)[:n]
+        assert engine.compress(data) == hdlz_oracle.compress(data)[1], (trial, n)
     engine.match10 = False
     engine.container = hz.CONTAINER_RAW
     try:
