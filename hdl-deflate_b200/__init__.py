@@ -89,8 +89,26 @@ class Engine(object):
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
+            for ptr, _ in getattr(self, "_pin", {}).values():
+                self._lib.hdlz_host_free_pinned(self._ctx, ptr)
+            self._pin = {}
             self._lib.hdlz_destroy(self._ctx)
             self._ctx = ctypes.c_void_p()
+
+    def _pinned(self, which, nbytes):
+        """A pinned staging buffer of the engine (grown on demand): single-stream calls copy through it, so the
+        device copies run at the link's rate and no fresh pages are touched per call."""
+        if not hasattr(self, "_pin"):
+            self._pin = {}
+        ptr, cap = self._pin.get(which, (None, 0))
+        if cap < nbytes:
+            if ptr is not None:
+                self._lib.hdlz_host_free_pinned(self._ctx, ptr)
+            cap = max(1 << 16, nbytes + nbytes // 4)
+            ptr = ctypes.c_void_p()
+            self._check(self._lib.hdlz_host_alloc_pinned(self._ctx, cap, ctypes.byref(ptr)))
+            self._pin[which] = (ptr, cap)
+        return ptr
 
     def __del__(self):
         try:
@@ -190,15 +208,14 @@ class Engine(object):
     def compress(self, data):
         """zlib stream of `data`, bit-identical to the reference's FAST+MATCH10 output."""
         data = bytes(data)
-        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
         cap = self.bound(len(data))
-        out = np.empty(cap, dtype=np.uint8)
+        src, out = self._pinned("in", max(len(data), 16)), self._pinned("out", cap)
+        ctypes.memmove(src, data, len(data))
         n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
-        self._check(self._lib.hdlz_compress_stream(self._ctx, src.ctypes.data, len(data), out.ctypes.data, cap,
-                                                   ctypes.byref(n), ctypes.byref(st)))
+        self._check(self._lib.hdlz_compress_stream(self._ctx, src, len(data), out, cap, ctypes.byref(n), ctypes.byref(st)))
         if st.value:
             raise StreamError(st.value)
-        return out[:n.value].tobytes()
+        return ctypes.string_at(out, n.value)
 
     def decompress(self, data, max_out=None, flags=0):
         """Inflate one zlib stream.  `max_out=None` grows the buffer until it fits (< 2^LMAX)."""

@@ -38,11 +38,12 @@ for n in (1 << 16, 1 << 20, 1 << 22, len(data)):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        eng.compress(d)                      # (grows the engine's pinned staging buffers)
         t0 = time.perf_counter()
         z = eng.compress(d)
         host_ms = (time.perf_counter() - t0) * 1e3
         assert int(d_st.item()) == 0 and int(d_len.item()) == len(z)
         assert bytes(d_out[:len(z)].cpu().numpy()) == z
-        print("%9d bytes  %-5s kernel %8.3f ms = %8.2f GB/s   host call (pageable) %8.2f ms   out %d"
+        print("%9d bytes  %-5s kernel %8.3f ms = %8.2f GB/s   Engine.compress %8.2f ms   out %d"
               % (n, mode, ms, n / ms / 1e6, host_ms, len(z)), flush=True)
 os.environ.pop("HDLZ_NO_LONG", None)
