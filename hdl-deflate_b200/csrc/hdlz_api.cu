@@ -264,10 +264,12 @@ int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, 
         return set_error(HDLZ_ERR_INVALID, "d_in/d_out must be 16-byte aligned and strides multiples of 16");
     if (!d_in_len && (uniform_len > in_stride || uniform_len >= (1u << HDLZ_LMAX)))
         return set_error(HDLZ_ERR_INVALID, "uniform_len %u does not fit in_stride / LMAX", uniform_len);
-    // a batch of ONE long stream: spread over the whole grid instead of one warp (same bytes)
-    if (n == 1 && !d_in_len && long_stream_ok(ctx, uniform_len) && compress_bound(uniform_len, ctx->container) <= out_stride)
-        return launch_compress_long(ctx, d_in, uniform_len, d_out, compress_bound(uniform_len, ctx->container), d_out_len,
-                                    d_status, (cudaStream_t)stream);
+    // a few long streams of one length: their tiles are spread over the whole grid instead of one warp per stream
+    // (same bytes); with more streams than resident warps the stream-per-warp kernel is as busy and has no look-back
+    if (!d_in_len && long_stream_ok(ctx, uniform_len) && n < (uint64_t)ctx->sm_count * 32 &&
+        compress_bound(uniform_len, ctx->container) <= out_stride)
+        return launch_compress_long(ctx, d_in, in_stride, uniform_len, d_out, out_stride, d_out_len, d_status, n,
+                                    (cudaStream_t)stream);
     return launch_compress(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n,
                            (cudaStream_t)stream);
 }

@@ -219,23 +219,28 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
     // device-wide queue head (one atomic per stream).  A static stride would leave the SM idle
     // wherever a CTA of the grid was not resident from the start and ran after the others.
     const uint64_t n_warps = kLong ? 0ull : (uint64_t)gridDim.x * kWarpsPerCta;
-    // kLong: `sid` is a TILE of the one stream and every tile comes from the queue head, the first one too: a tile
-    // may wait for its predecessors, so they must belong to warps that already run
-    const uint64_t n_tiles = kLong ? ((uint64_t)uniform_len + kTile - 1) / kTile : 0ull;
-    unsigned long long *lb_map = lbuf, *lb_bits = lbuf + n_tiles;
-    uint32_t *lb_adler = reinterpret_cast<uint32_t *>(lbuf + 2 * n_tiles);
+    // kLong: `sid` numbers the TILES of the streams (stream-major: all streams have `uniform_len` bytes) and every
+    // tile comes from the queue head, the first one too: a tile may wait for its predecessors in its stream, so
+    // they must belong to warps that already run
+    const uint64_t n_tiles = kLong ? ((uint64_t)uniform_len + kTile - 1) / kTile : 1ull;     // per stream
+    const uint64_t all_tiles = n_tiles * n_streams;
     uint64_t sid0 = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
     if constexpr (kLong) {
         unsigned long long tk0 = 0;
         if (lane == 0) tk0 = atomicAdd(queue, 1ull);
         sid0 = __shfl_sync(HDLZ_FULL_MASK, tk0, 0);
     }
-    for (uint64_t sid = sid0; sid < (kLong ? n_tiles : n_streams);) {
+    for (uint64_t sid = sid0; sid < (kLong ? all_tiles : n_streams);) {
         unsigned long long next_ticket = 0;
         if (lane == 0) next_ticket = atomicAdd(queue, 1ull);           // in flight while this stream is processed
+        const uint64_t ls = kLong ? sid / n_tiles : sid;               // the stream, and (kLong) the tile in it
+        const uint64_t lt = kLong ? sid - ls * n_tiles : 0ull;
+        // the stream's look-back arrays: one entry per tile
+        unsigned long long *lb_map = lbuf + ls * n_tiles, *lb_bits = lbuf + all_tiles + ls * n_tiles;
+        uint32_t *lb_adler = reinterpret_cast<uint32_t *>(lbuf + 2 * all_tiles) + ls * n_tiles;
         const uint32_t L = kLong ? uniform_len : in_len ? in_len[sid] : uniform_len;
-        const uint8_t *src = kLong ? in : in + sid * in_stride;
-        uint32_t *dst32 = reinterpret_cast<uint32_t *>(kLong ? out : out + sid * out_stride);
+        const uint8_t *src = in + ls * in_stride;
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + ls * out_stride);
         uint64_t need = 0;               // slot size this stream may need
         if constexpr (kMode == kModeFixed) need = compress_bound(L, container);
         else if constexpr (kMode == kModeTree)
@@ -281,8 +286,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
 
         uint32_t t_first = 0, t_stop = L;
         bool closing = true;             // this launch reaches the end of the stream
-        if constexpr (kLong) {           // exactly the tile `sid`
-            t_first = (uint32_t)sid * kTile;
+        if constexpr (kLong) {           // exactly the tile `lt`
+            t_first = (uint32_t)lt * kTile;
             t_stop = t_first + kTile < L ? t_first + kTile : L;
         }
         if (kStream) {
@@ -460,14 +465,14 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     const bool constant = __all_sync(HDLZ_FULL_MASK, lane >= 10 || mc == c0);
                     uint32_t cin = 0;
                     if (lane == 0) {
-                        const bool known = sid == 0 || constant;      // the carry-out does not depend on what comes in
-                        if (known) atomicExch(&lb_map[sid], kLbResolved | c0);
-                        else atomicExch(&lb_map[sid], kLbPartial | M);
-                        if (sid != 0) {
+                        const bool known = lt == 0 || constant;      // the carry-out does not depend on what comes in
+                        if (known) atomicExch(&lb_map[lt], kLbResolved | c0);
+                        else atomicExch(&lb_map[lt], kLbPartial | M);
+                        if (lt != 0) {
                             // look back: compose the maps of the predecessors until one of them knows its carry-out
                             // (or the composition has become constant)
                             unsigned long long comp = 0x9876543210ull;     // identity
-                            for (uint64_t j = sid - 1;; --j) {
+                            for (uint64_t j = lt - 1;; --j) {
                                 const unsigned long long v = lb_poll(&lb_map[j]);
                                 if ((v & kLbResolved) != 0ull) {
                                     cin = (uint32_t)(comp >> (4 * (v & 15ull))) & 15u;
@@ -488,7 +493,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                             }
                             if (!known) {
                                 __threadfence();
-                                atomicExch(&lb_map[sid], kLbResolved | ((M >> (4 * cin)) & 15ull));
+                                atomicExch(&lb_map[lt], kLbResolved | ((M >> (4 * cin)) & 15ull));
                             }
                         }
                     }
@@ -589,16 +594,16 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 // the tile's place in the stream: bits of all earlier tiles (after the header bits of tile 0)
                 unsigned long long b0 = 0;
                 if (lane == 0) {
-                    lb_adler[sid] = adler_a | (adler_b << 16);      // this tile's own sums (from a = 1, b = 0)
+                    lb_adler[lt] = adler_a | (adler_b << 16);      // this tile's own sums (from a = 1, b = 0)
                     __threadfence();
-                    if (sid == 0) atomicExch(&lb_bits[0], kLbResolved | (unsigned long long)(lbit + tile_bits));
-                    else atomicExch(&lb_bits[sid], kLbPartial | (unsigned long long)tile_bits);
+                    if (lt == 0) atomicExch(&lb_bits[0], kLbResolved | (unsigned long long)(lbit + tile_bits));
+                    else atomicExch(&lb_bits[lt], kLbPartial | (unsigned long long)tile_bits);
                 }
-                if (sid != 0) {
+                if (lt != 0) {
                     // look back 32 tiles at a time (lane l reads tile end - 1 - l): bit counts are added up to and
                     // including the nearest tile that already knows where it ends.  A whole wave of tiles computes
                     // at once, so a one-entry-at-a-time walk would be thousands of dependent reads long.
-                    for (uint64_t end = sid;; end -= 32) {
+                    for (uint64_t end = lt;; end -= 32) {
                         const bool in_range = end > (uint64_t)lane;
                         const unsigned long long v = in_range ? lb_poll(&lb_bits[end - 1 - lane]) : 0ull;
                         const uint32_t res = __ballot_sync(HDLZ_FULL_MASK, in_range && (v & kLbResolved) != 0ull);
@@ -611,7 +616,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     }
                     if (lane == 0) {
                         __threadfence();
-                        atomicExch(&lb_bits[sid], kLbResolved | (b0 + tile_bits));
+                        atomicExch(&lb_bits[lt], kLbResolved | (b0 + tile_bits));
                     }
                     pw = 0;
                     lbit = (uint32_t)(b0 & 31ull);
@@ -683,8 +688,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     // Adler-32 of the whole stream from the tiles' sums: (a1, b1, n1) then (a2, b2, n2) give
                     // a = a1 + a2 - 1, b = b1 + b2 + n2 (a1 - 1)  (mod 65521).  Every earlier tile is full.
                     // Each lane folds a run of tiles, lane 0 then folds the 32 runs and this tile.
-                    const uint64_t per = (sid + 31) / 32;
-                    const uint64_t j0 = per * lane < sid ? per * lane : sid, j1 = j0 + per < sid ? j0 + per : sid;
+                    const uint64_t per = (lt + 31) / 32;
+                    const uint64_t j0 = per * lane < lt ? per * lane : lt, j1 = j0 + per < lt ? j0 + per : lt;
                     uint32_t ra = 1, rb = 0;                       // 32-bit: b + b2 + 1024 * 65520 < 2^27
                     unsigned long long rn = 0;
                     for (uint64_t j = j0; j < j1; ++j) {
@@ -730,8 +735,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
                 const bool no_code = kMode == kModeTree && __any_sync(HDLZ_FULL_MASK, uncoded != 0u);
                 if (lane == 0) {
-                    out_len[kLong ? 0 : sid] = no_code ? 0u : 4 * wbase + nbytes + trailer;
-                    if (status) status[kLong ? 0 : sid] = no_code ? HDLZ_ST_NO_CODE : HDLZ_OK;
+                    out_len[ls] = no_code ? 0u : 4 * wbase + nbytes + trailer;
+                    if (status) status[ls] = no_code ? HDLZ_ST_NO_CODE : HDLZ_OK;
                 }
             }
         }
@@ -831,8 +836,8 @@ static int launch_mode(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, c
 
 // One long stream over the whole grid (k_compress<.., kLong = true>): hdlz_compress_stream for inputs of many
 // tiles.  d_out must hold compress_bound(len) bytes; it is zeroed here (tiles OR their border words into it).
-int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t len, uint8_t *d_out, uint64_t out_bytes,
-                         uint32_t *d_out_len, uint32_t *d_status, cudaStream_t s)
+int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, uint32_t len, uint8_t *d_out, uint64_t out_stride,
+                         uint32_t *d_out_len, uint32_t *d_status, uint64_t n, cudaStream_t s)
 {
     if (!ctx->long_attr_set) {
         HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
@@ -841,12 +846,12 @@ int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t len, uint8
         HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         ctx->long_attr_set = true;
     }
-    const uint64_t n_tiles = ((uint64_t)len + kTile - 1) / kTile;
+    const uint64_t n_tiles = (((uint64_t)len + kTile - 1) / kTile) * n;
     const size_t lb_bytes = n_tiles * (2 * sizeof(unsigned long long) + sizeof(uint32_t)) + 16;
     int rc = grow_device((void **)&ctx->d_long, &ctx->d_long_cap, lb_bytes);
     if (rc) return rc;
     HDLZ_CUDA(cudaMemsetAsync(ctx->d_long, 0, lb_bytes, s));
-    HDLZ_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, s));
+    HDLZ_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * out_stride, s));
     unsigned long long *queue = nullptr;
     if ((rc = next_queue(ctx, &queue, s))) return rc;
     uint64_t blocks = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -855,10 +860,10 @@ int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint32_t len, uint8
     unsigned long long *lbuf = reinterpret_cast<unsigned long long *>(ctx->d_long);
     if (ctx->max_match == 5)
         k_compress<5, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
-            d_in, 0, nullptr, len, d_out, 0, d_out_len, d_status, 1, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
+            d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
     else
         k_compress<10, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
-            d_in, 0, nullptr, len, d_out, 0, d_out_len, d_status, 1, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
+            d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;

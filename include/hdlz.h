@@ -209,7 +209,8 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
  * more is spread over the whole GPU, a tile of 1024 positions per warp (fixed tree, FAST, zlib / raw
  * container; otherwise one warp works through it): the parse position, the bit cursor and the Adler sums —
  * what the reference's FSM carries from byte to byte — cross the tile borders by look-back between the
- * warps, and the bytes are the same. */
+ * warps, and the bytes are the same.  hdlz_compress_batch does the same for a batch of fewer than 32 x SMs
+ * streams of one length (d_in_len == NULL) of HDLZ_LONG_STREAM bytes or more. */
 int hdlz_compress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
                          uint32_t *out_len, uint32_t *status);
 int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,

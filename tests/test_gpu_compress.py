@@ -411,6 +411,15 @@ def test_long_stream_over_the_grid(engine):
             have += len(piece)
         data = b"".join(parts)[:n]
         assert engine.compress(data) == hdlz_oracle.compress(data)[1], (trial, n)
+    # a few long streams of one length in one batch: their tiles share the grid, look-backs stay inside a stream
+    n, stride = 7, 200000
+    arr = np.frombuffer(mixed[:n * stride], dtype=np.uint8).reshape(n, stride).copy()
+    arr[3] = 0                                                           # one of them a run
+    arr[5, :100000] = np.frombuffer((b"abcdefg" * 15000)[:100000], dtype=np.uint8)
+    out, out_len, status = engine.compress_host(arr)
+    assert not status.any()
+    for i in range(n):
+        assert out[i, :out_len[i]].tobytes() == hdlz_oracle.compress(arr[i].tobytes())[1], i
     engine.match10 = False
     engine.container = hz.CONTAINER_RAW
     try:
