@@ -625,9 +625,9 @@ __device__ __forceinline__ void range_masks(uint32_t start, uint32_t n, uint32_t
 {
     w = start >> 5;
     const uint32_t sh = start & 31u;
-    const unsigned long long m = ((n >= 32u ? 0xFFFFFFFFull : ((1ull << n) - 1ull))) << sh;
-    m0 = (uint32_t)m;
-    m1 = (uint32_t)(m >> 32);
+    const uint32_t full = n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u;
+    m0 = full << sh;
+    m1 = sh ? full >> (32u - sh) : 0u;                   // the bits that spill into the next word
 }
 
 __device__ __forceinline__ bool range_clear(const uint32_t *bm, uint32_t start, uint32_t n)      // n <= 32
