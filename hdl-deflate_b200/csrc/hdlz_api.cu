@@ -69,12 +69,11 @@ static inline uint64_t host_chunk(uint64_t n, uint64_t bytes_per_item)
     return c < n ? c : n;
 }
 
-// the long-stream compress kernel codes with the fixed tree, the FAST window and the zlib / raw containers
+// the long-stream compress kernel codes with the fixed or the installed tree, the FAST window and the zlib / raw containers
 // (HDLZ_NO_LONG: A/B runs of tools/ and tests/)
 static inline bool long_stream_ok(const hdlz_ctx *ctx, uint32_t len)
 {
-    return len >= HDLZ_LONG_STREAM && !ctx->tree_set && ctx->window == HDLZ_CWINDOW && ctx->container != HDLZ_CONTAINER_GZIP &&
-           !getenv("HDLZ_NO_LONG");
+    return len >= HDLZ_LONG_STREAM && ctx->window == HDLZ_CWINDOW && ctx->container != HDLZ_CONTAINER_GZIP && !getenv("HDLZ_NO_LONG");
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -266,8 +265,8 @@ int hdlz_compress_batch(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, 
         return set_error(HDLZ_ERR_INVALID, "uniform_len %u does not fit in_stride / LMAX", uniform_len);
     // a few long streams of one length: their tiles are spread over the whole grid instead of one warp per stream
     // (same bytes); with more streams than resident warps the stream-per-warp kernel is as busy and has no look-back
-    if (!d_in_len && long_stream_ok(ctx, uniform_len) && n < (uint64_t)ctx->sm_count * 32 &&
-        compress_bound(uniform_len, ctx->container) <= out_stride)
+    if (!d_in_len && long_stream_ok(ctx, uniform_len) && n < (uint64_t)ctx->sm_count * 32 && !refresh_tree(ctx) &&
+        (ctx->tree_set ? tree_bound(ctx, uniform_len) : compress_bound(uniform_len, ctx->container)) <= out_stride)
         return launch_compress_long(ctx, d_in, in_stride, uniform_len, d_out, out_stride, d_out_len, d_status, n,
                                     (cudaStream_t)stream);
     return launch_compress(ctx, d_in, in_stride, d_in_len, uniform_len, d_out, out_stride, d_out_len, d_status, n,

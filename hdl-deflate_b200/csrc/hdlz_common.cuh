@@ -42,7 +42,7 @@ struct hdlz_ctx {
     bool wide_attr_set;
     bool stream_attr_set;
     bool tree_attr_set;
-    bool long_attr_set;
+    bool long_attr_set, long_tree_attr_set;
     void *d_long;          // look-back arrays of the long-stream compress kernel (one entry per tile)
     size_t d_long_cap;
     // application / trained code (hdlz_set_tree, hdlz_train_tree); tree_set false = the reference's fixed code

@@ -185,7 +185,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
            uint32_t container, StreamCtl *ctl, const TreeDev *__restrict__ tree, unsigned long long *hist,
            unsigned long long *lbuf = nullptr)
 {
-    static_assert(!kLong || (!kStream && kMode == kModeFixed), "the long-stream mode codes with the fixed tree");
+    static_assert(!kLong || (!kStream && kMode != kModeHist), "the long-stream mode: batch calls, fixed or installed tree");
     extern __shared__ uint4 smem_raw[];
     uint32_t *LT = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *DC = LT + 256;
@@ -238,6 +238,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         // the stream's look-back arrays: one entry per tile
         unsigned long long *lb_map = lbuf + ls * n_tiles, *lb_bits = lbuf + all_tiles + ls * n_tiles;
         uint32_t *lb_adler = reinterpret_cast<uint32_t *>(lbuf + 2 * all_tiles) + ls * n_tiles;
+        uint32_t *lb_flag = reinterpret_cast<uint32_t *>(lbuf + 2 * all_tiles) + all_tiles + ls;      // kModeTree: a tile met a symbol without a code
         const uint32_t L = kLong ? uniform_len : in_len ? in_len[sid] : uniform_len;
         const uint8_t *src = in + ls * in_stride;
         uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + ls * out_stride);
@@ -265,7 +266,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         if constexpr (kMode == kModeTree) {
             // container header, BFINAL = 1 / BTYPE = 10 and the code description: the same bits in every stream
             const uint32_t nfp = tree->prefix_bits >> 5;
-            for (uint32_t k = lane; k < nfp; k += 32) dst32[k] = tree->prefix[k];
+            if (!kLong || lt == 0)
+                for (uint32_t k = lane; k < nfp; k += 32) dst32[k] = tree->prefix[k];
             pw = tree->prefix[nfp];
             lbit = tree->prefix_bits & 31u;
             wbase = nfp;
@@ -593,10 +595,12 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             if constexpr (kLong) {
                 // the tile's place in the stream: bits of all earlier tiles (after the header bits of tile 0)
                 unsigned long long b0 = 0;
+                const bool tile_uncoded = kMode == kModeTree && __any_sync(HDLZ_FULL_MASK, uncoded != 0u);
                 if (lane == 0) {
                     lb_adler[lt] = adler_a | (adler_b << 16);      // this tile's own sums (from a = 1, b = 0)
+                    if (tile_uncoded) atomicOr(lb_flag, 1u);
                     __threadfence();
-                    if (lt == 0) atomicExch(&lb_bits[0], kLbResolved | (unsigned long long)(lbit + tile_bits));
+                    if (lt == 0) atomicExch(&lb_bits[0], kLbResolved | (32ull * wbase + lbit + tile_bits));
                     else atomicExch(&lb_bits[lt], kLbPartial | (unsigned long long)tile_bits);
                 }
                 if (lt != 0) {
@@ -733,7 +737,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     if (kLong && k == 0 && lbit != 0) atomicOr(&dst32[wbase], outw[0]);      // shared with the tile before
                     else dst32[wbase + k] = outw[k];
                 }
-                const bool no_code = kMode == kModeTree && __any_sync(HDLZ_FULL_MASK, uncoded != 0u);
+                bool no_code = kMode == kModeTree && __any_sync(HDLZ_FULL_MASK, uncoded != 0u);
+                if (kLong && kMode == kModeTree) no_code = no_code || *reinterpret_cast<const volatile uint32_t *>(lb_flag) != 0u;
                 if (lane == 0) {
                     out_len[ls] = no_code ? 0u : 4 * wbase + nbytes + trailer;
                     if (status) status[ls] = no_code ? HDLZ_ST_NO_CODE : HDLZ_OK;
@@ -836,18 +841,20 @@ static int launch_mode(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, c
 
 // One long stream over the whole grid (k_compress<.., kLong = true>): hdlz_compress_stream for inputs of many
 // tiles.  d_out must hold compress_bound(len) bytes; it is zeroed here (tiles OR their border words into it).
-int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, uint32_t len, uint8_t *d_out, uint64_t out_stride,
-                         uint32_t *d_out_len, uint32_t *d_status, uint64_t n, cudaStream_t s)
+template <int kMode>
+static int launch_long_mode(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, uint32_t len, uint8_t *d_out, uint64_t out_stride,
+                            uint32_t *d_out_len, uint32_t *d_status, uint64_t n, cudaStream_t s)
 {
-    if (!ctx->long_attr_set) {
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
-        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        ctx->long_attr_set = true;
+    bool &attr = kMode == kModeFixed ? ctx->long_attr_set : ctx->long_tree_attr_set;
+    if (!attr) {
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kMode, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kMode>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kMode, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kMode, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kMode>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kMode, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
     }
     const uint64_t n_tiles = (((uint64_t)len + kTile - 1) / kTile) * n;
-    const size_t lb_bytes = n_tiles * (2 * sizeof(unsigned long long) + sizeof(uint32_t)) + 16;
+    const size_t lb_bytes = n_tiles * (2 * sizeof(unsigned long long) + sizeof(uint32_t)) + n * sizeof(uint32_t) + 16;
     int rc = grow_device((void **)&ctx->d_long, &ctx->d_long_cap, lb_bytes);
     if (rc) return rc;
     HDLZ_CUDA(cudaMemsetAsync(ctx->d_long, 0, lb_bytes, s));
@@ -859,14 +866,25 @@ int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride,
     if (blocks > resident) blocks = resident;
     unsigned long long *lbuf = reinterpret_cast<unsigned long long *>(ctx->d_long);
     if (ctx->max_match == 5)
-        k_compress<5, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
-            d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
+        k_compress<5, false, kMode, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kMode>(), s>>>(
+            d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, ctx->d_tree, nullptr, lbuf);
     else
-        k_compress<10, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
-            d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, nullptr, nullptr, lbuf);
+        k_compress<10, false, kMode, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kMode>(), s>>>(
+            d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, ctx->d_tree, nullptr, lbuf);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;
+}
+
+int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, uint32_t len, uint8_t *d_out, uint64_t out_stride,
+                         uint32_t *d_out_len, uint32_t *d_status, uint64_t n, cudaStream_t s)
+{
+    if (ctx->tree_set) {
+        const int rc = refresh_tree(ctx);
+        if (rc) return rc;
+        return launch_long_mode<kModeTree>(ctx, d_in, in_stride, len, d_out, out_stride, d_out_len, d_status, n, s);
+    }
+    return launch_long_mode<kModeFixed>(ctx, d_in, in_stride, len, d_out, out_stride, d_out_len, d_status, n, s);
 }
 
 // hdlz_train_tree: the symbols of the reference's parse over the batch, counted into d_hist[kTreeHistWords]

@@ -206,8 +206,8 @@ int hdlz_compress_host_packed(hdlz_ctx *ctx, const uint8_t *in, uint64_t in_stri
 
 /* One stream of any length < 2^24 (LMAX): exactly what one STARTC / STARTD job of the
  * port protocol does.  `status` receives the hdlz_status.  A compress stream of HDLZ_LONG_STREAM bytes or
- * more is spread over the whole GPU, a tile of 1024 positions per warp (fixed tree, FAST, zlib / raw
- * container; otherwise one warp works through it): the parse position, the bit cursor and the Adler sums —
+ * more is spread over the whole GPU, a tile of 1024 positions per warp (fixed or installed tree, FAST, zlib /
+ * raw container; otherwise one warp works through it): the parse position, the bit cursor and the Adler sums —
  * what the reference's FSM carries from byte to byte — cross the tile borders by look-back between the
  * warps, and the bytes are the same.  hdlz_compress_batch does the same for a batch of fewer than 32 x SMs
  * streams of one length (d_in_len == NULL) of HDLZ_LONG_STREAM bytes or more. */

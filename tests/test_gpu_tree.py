@@ -155,3 +155,30 @@ def test_long_stream_and_worst_case_bound(eng):
     # a slot smaller than the bound is refused, not overrun
     out, out_len, status = eng.compress_host(arr, out_stride=2320)
     assert status[0] == 6 and out_len[0] == 0
+
+
+def test_long_stream_with_a_tree(eng):
+    """The long-stream kernel (one stream over the whole grid) with an installed tree: the same bytes as the
+    restatement, and a symbol without a code in a late tile fails the whole stream."""
+    rnd = random.Random(24)
+    data = b"".join(text_blocks(rnd, 1, 300001, b"ACGTN acgt\n"))
+    arr = np.frombuffer(data[:294912], dtype=np.uint8).reshape(144, 2048)
+    lit, dist = eng.train_tree(arr)
+    got = eng.compress(data)
+    st, want = T.compress(data, list(lit), list(dist))
+    assert st == 0 and got == want and zlib.decompress(got) == data
+    assert len(got) < 0.7 * len(O.compress(data)[1])
+    eng.container = hz.CONTAINER_RAW
+    st, want = T.compress(data, list(lit), list(dist), container=1)
+    assert eng.compress(data) == want
+    eng.container = hz.CONTAINER_ZLIB
+    # a code without 'Z': one 'Z' far into the stream
+    keep = set(b"ACGTN acgt\n") | set(range(256, 265))
+    lit2 = T.limited_lengths([1 if s in keep else 0 for s in range(286)], 15)
+    eng.set_tree(lit2, list(dist))
+    assert zlib.decompress(eng.compress(data)) == data
+    bad = bytearray(data)
+    bad[250000] = ord("Z")
+    with pytest.raises(hz.StreamError) as e:
+        eng.compress(bytes(bad))
+    assert e.value.status == 11
