@@ -594,13 +594,23 @@ int cstream_run(hdlz_cstream *st, bool closing, uint8_t *out, uint32_t out_cap, 
     HDLZ_CUDA(cudaMemcpyAsync(st->d_ctl, &st->h_ctl, sizeof(hdlz::StreamCtl), cudaMemcpyHostToDevice, s));
     HDLZ_CUDA(cudaMemsetAsync(st->d_queue, 0, sizeof(unsigned long long), s));
     HDLZ_CUDA(cudaMemsetAsync(st->d_small, 0, 2 * sizeof(uint32_t), s));
-    int rc = launch_compress_stream(ctx, st->d_buf[st->cur] - st->base, st->received, st->d_out, st->d_small, st->d_small + 1,
-                                    st->d_ctl, st->d_queue, s);
+    // a piece of many tiles goes over the whole grid (k_compress<.., kLong> with the state in *d_ctl), a short one to one warp
+    const uint64_t tiles = closing ? ((uint64_t)(st->received - st->t0) + kCsTile - 1) / kCsTile : (t_end - st->t0) / kCsTile;
+    const bool spread = tiles >= HDLZ_LONG_STREAM / kCsTile && !getenv("HDLZ_NO_LONG");
+    int rc = spread ? launch_compress_piece(ctx, st->d_buf[st->cur] - st->base, st->received, tiles, st->d_out, kCsOut, st->d_small,
+                                            st->d_small + 1, st->d_ctl, s)
+                    : launch_compress_stream(ctx, st->d_buf[st->cur] - st->base, st->received, st->d_out, st->d_small, st->d_small + 1,
+                                             st->d_ctl, st->d_queue, s);
     if (rc) return rc;
     uint32_t small[2] = {0, 0};
     HDLZ_CUDA(cudaMemcpyAsync(&st->h_ctl, st->d_ctl, sizeof(hdlz::StreamCtl), cudaMemcpyDeviceToHost, s));
     HDLZ_CUDA(cudaMemcpyAsync(small, st->d_small, sizeof small, cudaMemcpyDeviceToHost, s));
     HDLZ_CUDA(cudaStreamSynchronize(s));
+    if (spread && !closing) {
+        // the partial word after the whole ones stays in the launch's output: it is the next launch's `pw`
+        HDLZ_CUDA(cudaMemcpyAsync(&st->h_ctl.pw, st->d_out + 4u * (size_t)st->h_ctl.out_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        HDLZ_CUDA(cudaStreamSynchronize(s));
+    }
     const uint32_t nbytes = closing ? small[0] : 4u * st->h_ctl.out_words;
     if (nbytes > out_cap) return set_error(HDLZ_ERR_INVALID, "stream output needs %u bytes, out_cap is %u", nbytes, out_cap);
     if (nbytes) HDLZ_CUDA(cudaMemcpyAsync(out, st->d_out, nbytes, cudaMemcpyDeviceToHost, s));

@@ -156,6 +156,8 @@ int launch_compress(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
                     uint32_t *d_status, uint64_t n, cudaStream_t s);
 int launch_compress_long(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, uint32_t len, uint8_t *d_out, uint64_t out_stride,
                          uint32_t *d_out_len, uint32_t *d_status, uint64_t n, cudaStream_t s);
+int launch_compress_piece(hdlz_ctx *ctx, const uint8_t *d_in_virtual, uint32_t received, uint64_t n_tiles, uint8_t *d_out,
+                          uint64_t out_bytes, uint32_t *d_out_len, uint32_t *d_status, StreamCtl *d_ctl, cudaStream_t s);
 int launch_compress_hist(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len, uint32_t uniform_len,
                          uint64_t n, unsigned long long *d_hist, cudaStream_t s);
 int refresh_tree(hdlz_ctx *ctx);

@@ -222,7 +222,16 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
     // kLong: `sid` numbers the TILES of the streams (stream-major: all streams have `uniform_len` bytes) and every
     // tile comes from the queue head, the first one too: a tile may wait for its predecessors in its stream, so
     // they must belong to warps that already run
-    const uint64_t n_tiles = kLong ? ((uint64_t)uniform_len + kTile - 1) / kTile : 1ull;     // per stream
+    // kLong with `ctl`: one PIECE of a stream fed in pieces (hdlz_cstream_*): the tiles [ctl->t0, ctl->t_end) — or
+    // to the end of the stream when ctl->final — of which `uniform_len` bytes have arrived; tile 0 takes carry,
+    // partial word and Adler sums from *ctl, the last tile leaves them there (the partial word stays in `out`).
+    uint32_t pc_t0 = 0, pc_final = 1;
+    uint64_t n_tiles = kLong ? ((uint64_t)uniform_len + kTile - 1) / kTile : 1ull;     // per stream
+    if (kLong && ctl) {
+        pc_t0 = ctl->t0;
+        pc_final = ctl->final;
+        n_tiles = pc_final ? ((uint64_t)(uniform_len - pc_t0) + kTile - 1) / kTile : (ctl->t_end - pc_t0) / kTile;
+    }
     const uint64_t all_tiles = n_tiles * n_streams;
     uint64_t sid0 = (uint64_t)blockIdx.x * kWarpsPerCta + warp;
     if constexpr (kLong) {
@@ -289,8 +298,14 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
         uint32_t t_first = 0, t_stop = L;
         bool closing = true;             // this launch reaches the end of the stream
         if constexpr (kLong) {           // exactly the tile `lt`
-            t_first = (uint32_t)lt * kTile;
+            t_first = pc_t0 + (uint32_t)lt * kTile;
             t_stop = t_first + kTile < L ? t_first + kTile : L;
+            closing = pc_final != 0;
+            if (lt == 0 && pc_t0 != 0) {                 // a later piece: the partial word the previous one left
+                pw = ctl->pw;
+                lbit = ctl->lbit;
+                wbase = 0;
+            }
         }
         if (kStream) {
             t_first = ctl->t0;
@@ -468,7 +483,8 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     uint32_t cin = 0;
                     if (lane == 0) {
                         const bool known = lt == 0 || constant;      // the carry-out does not depend on what comes in
-                        if (known) atomicExch(&lb_map[lt], kLbResolved | c0);
+                        if (lt == 0 && pc_t0 != 0) cin = ctl->carry;
+                        if (known) atomicExch(&lb_map[lt], kLbResolved | (constant ? c0 : (uint32_t)(M >> (4 * cin)) & 15u));
                         else atomicExch(&lb_map[lt], kLbPartial | M);
                         if (lt != 0) {
                             // look back: compose the maps of the predecessors until one of them knows its carry-out
@@ -656,6 +672,37 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
             }
             __syncwarp();
 
+            // kLong: Adler-32 of everything up to and including this tile from the tiles' sums: (a1, b1, n1) then
+            // (a2, b2, n2) give a = a1 + a2 - 1, b = b1 + b2 + n2 (a1 - 1)  (mod 65521).  Every earlier tile of the
+            // launch is full.  Each lane folds a run of tiles, then the 32 runs and this tile are folded onto what the
+            // earlier pieces left (1, 0 at the start of a stream).  Called by the last tile of a launch.
+            auto fold_adler = [&]() {
+                const uint64_t per = (lt + 31) / 32;
+                const uint64_t j0 = per * lane < lt ? per * lane : lt, j1 = j0 + per < lt ? j0 + per : lt;
+                uint32_t ra = 1, rb = 0;                       // 32-bit: b + b2 + 1024 * 65520 < 2^27
+                unsigned long long rn = 0;
+                for (uint64_t j = j0; j < j1; ++j) {
+                    const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(&lb_adler[j]);
+                    const uint32_t a2 = v & 0xFFFFu, b2 = v >> 16;
+                    rb = (rb + b2 + (uint32_t)kTile * ((ra + 65520u) % 65521u)) % 65521u;
+                    ra = (ra + a2 + 65520u) % 65521u;
+                    rn += kTile;
+                }
+                unsigned long long fa = 1, fb = 0;
+                if (pc_t0 != 0) {
+                    fa = ctl->adler_a;
+                    fb = ctl->adler_b;
+                }
+                for (int l = 0; l < 32; ++l) {
+                    const unsigned long long a2 = __shfl_sync(HDLZ_FULL_MASK, ra, l), b2 = __shfl_sync(HDLZ_FULL_MASK, rb, l);
+                    const unsigned long long n2 = __shfl_sync(HDLZ_FULL_MASK, rn, l);
+                    fb = (fb + b2 + (n2 % 65521ull) * (fa + 65520ull)) % 65521ull;
+                    fa = (fa + a2 + 65520ull) % 65521ull;
+                }
+                const unsigned long long ta = adler_a, tb = adler_b;         // this tile's own
+                adler_b = (uint32_t)((fb + tb + (unsigned long long)(n_tile % 65521u) * (fa + 65520ull)) % 65521ull);
+                adler_a = (uint32_t)((fa + ta + 65520ull) % 65521ull);
+            };
             // ---------------- flush ---------------------------------------------------------------------
             uint32_t total = lbit + tile_bits;
             if (kLong && !last_tile) {
@@ -667,6 +714,17 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                     else dst32[wbase + k] = outw[k];
                 }
                 if (lane == 0 && (total & 31u) != 0u) atomicOr(&dst32[wbase + nfull], outw[nfull]);
+                if (ctl && !closing && lt + 1 == n_tiles) {      // the piece ends here: what the next one starts from
+                    fold_adler();
+                    if (lane == 0) {
+                        ctl->carry = carry;
+                        ctl->adler_a = adler_a;
+                        ctl->adler_b = adler_b;
+                        ctl->lbit = total & 31u;
+                        ctl->out_words = wbase + nfull;          // the partial word after them stays in `out` for the host
+                        ctl->t0 = t_stop;
+                    }
+                }
             } else if (!last_tile) {
                 const uint32_t nfull = total >> 5;
                 for (uint32_t k = lane; k < nfull; k += 32) dst32[wbase + k] = outw[k];
@@ -688,32 +746,7 @@ k_compress(const uint8_t *__restrict__ in, uint64_t in_stride, const uint32_t *_
                 }
                 const uint32_t nbytes = (total + 7) >> 3;     // pad to a byte (deflate.py:784-787)
                 uint32_t trailer = 4;
-                if constexpr (kLong) {
-                    // Adler-32 of the whole stream from the tiles' sums: (a1, b1, n1) then (a2, b2, n2) give
-                    // a = a1 + a2 - 1, b = b1 + b2 + n2 (a1 - 1)  (mod 65521).  Every earlier tile is full.
-                    // Each lane folds a run of tiles, lane 0 then folds the 32 runs and this tile.
-                    const uint64_t per = (lt + 31) / 32;
-                    const uint64_t j0 = per * lane < lt ? per * lane : lt, j1 = j0 + per < lt ? j0 + per : lt;
-                    uint32_t ra = 1, rb = 0;                       // 32-bit: b + b2 + 1024 * 65520 < 2^27
-                    unsigned long long rn = 0;
-                    for (uint64_t j = j0; j < j1; ++j) {
-                        const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(&lb_adler[j]);
-                        const uint32_t a2 = v & 0xFFFFu, b2 = v >> 16;
-                        rb = (rb + b2 + (uint32_t)kTile * ((ra + 65520u) % 65521u)) % 65521u;
-                        ra = (ra + a2 + 65520u) % 65521u;
-                        rn += kTile;
-                    }
-                    unsigned long long fa = 1, fb = 0;
-                    for (int l = 0; l < 32; ++l) {
-                        const unsigned long long a2 = __shfl_sync(HDLZ_FULL_MASK, ra, l), b2 = __shfl_sync(HDLZ_FULL_MASK, rb, l);
-                        const unsigned long long n2 = __shfl_sync(HDLZ_FULL_MASK, rn, l);
-                        fb = (fb + b2 + (n2 % 65521ull) * (fa + 65520ull)) % 65521ull;
-                        fa = (fa + a2 + 65520ull) % 65521ull;
-                    }
-                    const unsigned long long ta = adler_a, tb = adler_b;         // this tile's own
-                    adler_b = (uint32_t)((fb + tb + (unsigned long long)(n_tile % 65521u) * (fa + 65520ull)) % 65521ull);
-                    adler_a = (uint32_t)((fa + ta + 65520ull) % 65521ull);
-                }
+                if constexpr (kLong) fold_adler();
                 if (lane == 0) {
                     uint8_t *ob = reinterpret_cast<uint8_t *>(outw);
                     if (container == HDLZ_CONTAINER_ZLIB) {
@@ -871,6 +904,40 @@ static int launch_long_mode(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stri
     else
         k_compress<10, false, kMode, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kMode>(), s>>>(
             d_in, in_stride, nullptr, len, d_out, out_stride, d_out_len, d_status, n, queue, ctx->container, nullptr, ctx->d_tree, nullptr, lbuf);
+    ctx->launches++;
+    HDLZ_CUDA(cudaGetLastError());
+    return HDLZ_SUCCESS;
+}
+
+// One piece of a stream fed in pieces, many tiles of it: the long-stream kernel with the state in *d_ctl
+// (hdlz_cstream_feed / _finish).  d_out (out_bytes, zeroed here) receives this launch's words.
+int launch_compress_piece(hdlz_ctx *ctx, const uint8_t *d_in_virtual, uint32_t received, uint64_t n_tiles, uint8_t *d_out,
+                          uint64_t out_bytes, uint32_t *d_out_len, uint32_t *d_status, StreamCtl *d_ctl, cudaStream_t s)
+{
+    if (!ctx->long_attr_set) {
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<10, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<kModeFixed>()));
+        HDLZ_CUDA(cudaFuncSetAttribute(k_compress<5, false, kModeFixed, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->long_attr_set = true;
+    }
+    const size_t lb_bytes = n_tiles * (2 * sizeof(unsigned long long) + sizeof(uint32_t)) + sizeof(uint32_t) + 16;
+    int rc = grow_device((void **)&ctx->d_long, &ctx->d_long_cap, lb_bytes);
+    if (rc) return rc;
+    HDLZ_CUDA(cudaMemsetAsync(ctx->d_long, 0, lb_bytes, s));
+    HDLZ_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, s));
+    unsigned long long *queue = nullptr;
+    if ((rc = next_queue(ctx, &queue, s))) return rc;
+    uint64_t blocks = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    const uint64_t resident = (uint64_t)ctx->sm_count * kCtasPerSm;
+    if (blocks > resident) blocks = resident;
+    unsigned long long *lbuf = reinterpret_cast<unsigned long long *>(ctx->d_long);
+    if (ctx->max_match == 5)
+        k_compress<5, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
+            d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status, 1, queue, ctx->container, d_ctl, nullptr, nullptr, lbuf);
+    else
+        k_compress<10, false, kModeFixed, true><<<(unsigned)blocks, kWarpsPerCta * 32, smem_bytes<kModeFixed>(), s>>>(
+            d_in_virtual, 0, nullptr, received, d_out, 0, d_out_len, d_status, 1, queue, ctx->container, d_ctl, nullptr, nullptr, lbuf);
     ctx->launches++;
     HDLZ_CUDA(cudaGetLastError());
     return HDLZ_SUCCESS;

@@ -229,6 +229,8 @@ int hdlz_decompress_stream(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8
  *           which the stream is encoded (the reference's o_iprogress).
  *   finish: no more input (the reference's IDLE after START): the rest of the stream, EOB, Adler-32.
  *           *status as hdlz_compress_stream (HDLZ_ST_SHORT_INPUT for fewer than 5 bytes in total). */
+/* (a piece that completes 64 tiles or more is encoded by the whole GPU, like hdlz_compress_stream of a long input;
+ * smaller pieces by one warp — the bytes are the same either way) */
 typedef struct hdlz_cstream hdlz_cstream;
 int hdlz_cstream_begin(hdlz_ctx *ctx, hdlz_cstream **stream);
 int hdlz_cstream_feed(hdlz_cstream *stream, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,

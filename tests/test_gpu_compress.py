@@ -357,6 +357,22 @@ def test_stream_fed_in_pieces(engine):
             got += s.finish()
             assert bytes(got) == hdlz_oracle.compress(data)[1], (trial, L)
         s.close()
+    # big pieces: a piece of 64 tiles or more is encoded by the whole grid (the long-stream kernel with the state of
+    # the stream in its control record), smaller ones by one warp; both kinds mixed in one stream
+    huge = b"".join(workload.blocks(9100, 1536, 2048)) + bytes(200000) + (b"abcdefg" * 40000)      # 3.6 MB
+    want = hdlz_oracle.compress(huge)[1]
+    for sizes in ([262144], [1 << 20], [700000, 5, 100000, 70000, 33, 300000], [65536 + 34, 2048]):
+        s = engine.compress_stream()
+        got, pos, k = bytearray(), 0, 0
+        while pos < len(huge):
+            n = sizes[k % len(sizes)]
+            got += s.feed(huge[pos:pos + n])
+            assert s.in_progress <= pos + n
+            pos += n
+            k += 1
+        got += s.finish()
+        s.close()
+        assert bytes(got) == want, sizes
     engine.match10 = False
     engine.container = hz.CONTAINER_RAW
     try:
