@@ -372,6 +372,51 @@ def run_tree(eng, hz, d_plain, n, dev, stream, steps):
     return out
 
 
+def run_long_stream(eng, hz, d_plain, dev, stream, steps, nbytes=4 << 20):
+    """ONE compress stream (the reference's own use: one stream at a time): the first 4 MiB of the blocks as a
+    single stream through hdlz_compress_batch with n = 1 — spread over the whole grid (k_compress<.., kLong>) and,
+    for comparison, on one warp (HDLZ_NO_LONG=1).  The two outputs are compared, and the stream is inflated again
+    by the engine (Adler-32 verified) and compared with the input."""
+    import torch
+    src = d_plain.view(-1)[:nbytes].contiguous()
+    cap = hz.compress_bound(nbytes)
+    outs, res = [], {}
+    for mode in ("grid", "one_warp"):
+        if mode == "one_warp":
+            os.environ["HDLZ_NO_LONG"] = "1"
+        d_out = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        d_len = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_st = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def run():
+            eng.compress_batch(src, nbytes, None, nbytes, d_out, cap, d_len, d_st, 1, stream=stream)
+        try:
+            ms, best = _time_launches(run, steps if mode == "grid" else 2, warmup=1)
+        finally:
+            os.environ.pop("HDLZ_NO_LONG", None)
+        assert int(d_st.item()) == 0, "long stream: status"
+        outs.append(d_out[:int(d_len.item())].clone())
+        res[mode + "_ms"] = ms
+        res[mode + "_gbps"] = nbytes / (ms * 1e-3) / 1e9
+    assert torch.equal(outs[0], outs[1]), "long stream: grid and one-warp outputs differ"
+    n = outs[0].numel()
+    d_in = torch.zeros((n + 31) & ~15, dtype=torch.uint8, device=dev)
+    d_in[:n] = outs[0]
+    d_back = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    d_blen = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_bst = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_clen = torch.tensor([n], dtype=torch.int32, device=dev)
+    eng.decompress_batch(d_in, None, d_in.numel(), d_clen, d_back, nbytes, nbytes, d_blen, d_bst, 1,
+                         flags=hz.F_VERIFY_ADLER, stream=stream)
+    torch.cuda.synchronize()
+    assert int(d_bst.item()) == 0 and torch.equal(d_back, src), "long stream: round trip"
+    res.update({"bytes": nbytes, "compressed_bytes": n, "round_trip_verified": True,
+                "what": "one %d-byte stream, hdlz_compress_batch with n = 1: tiles of the stream over the whole grid "
+                        "(parse carry, bit cursor and Adler sums across tile borders by look-back) against one warp; "
+                        "same bytes" % nbytes})
+    return res
+
+
 def config4_plain(nd, L=32768, seed=4):
     """Plain side of configs[3]: Zipf-like bytes over 64 symbols with repeats at distances up to 32 KiB
     (SURVEY 8(d)); compressible enough that zlib level 6 emits dynamic blocks."""
@@ -825,6 +870,7 @@ def main():
         cfgs["config4"] = run_config4(eng, hz, args.c4_streams, min(args.c4_distinct, args.c4_streams), dev, stream,
                                       max(3, args.steps // 2), threads, peak)
         cfgs["tree"] = run_tree(eng, hz, d_in, n, dev, stream, max(3, args.steps // 2))
+        cfgs["long_stream"] = run_long_stream(eng, hz, d_in, dev, stream, max(3, args.steps // 2))
         line["configs"] = cfgs
 
     print(json.dumps(line), flush=True)
