@@ -84,7 +84,9 @@ def test_c_client_builds_and_runs(tmp_path):
     out = p.stdout
     assert p.returncode == 0, out + p.stderr
     assert "version 000100" in out and "bound2048 2320 2320 2336" in out and "status4 DIST_TOO_FAR" in out
+    assert "tree 0 lenA" in out and "head 789c" in out            # device-independent helpers of the tree-coded mode
     if torch.cuda.is_available():
         assert "compress 0 status 0" in out and "head 789c" in out and "same 1" in out
+        assert "dstream 0 status 0" in out and "remaining 0 same 1" in out
     else:
         assert "devices 0" in out and "create -" in out

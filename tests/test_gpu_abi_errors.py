@@ -56,7 +56,8 @@ def test_options_round_trip(engine):
 
 
 def test_c_client_runs_a_job(tmp_path):
-    """tests/c/abi_example.c (plain C against include/hdlz.h) compresses and inflates one stream."""
+    """tests/c/abi_example.c (plain C against include/hdlz.h) compresses and inflates one stream, in one call and
+    through hdlz_dstream_* in pieces."""
     import os
     import shutil
     import subprocess
@@ -72,3 +73,4 @@ def test_c_client_runs_a_job(tmp_path):
     p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "compress 0 status 0" in p.stdout and "head 789c" in p.stdout and "same 1" in p.stdout
+    assert "dstream 0 status 0" in p.stdout and "remaining 0 same 1" in p.stdout, p.stdout      # inflated in 7-byte pieces
