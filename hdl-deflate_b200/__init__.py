@@ -217,6 +217,19 @@ class Engine(object):
             raise StreamError(st.value)
         return ctypes.string_at(out, n.value)
 
+    def compress_dynamic(self, data):
+        """One stream coded with its own Huffman tree (hdlz_compress_stream_dyn): statistics counted on the GPU over
+        the stream's 2 KiB blocks, one BTYPE = 10 block, the reference's parse."""
+        data = bytes(data)
+        cap = compress_bound(len(data), self.container) + 2 * len(data) + 512      # a 15-bit code is the worst case
+        src, out = self._pinned("in", max(len(data), 16)), self._pinned("out", cap)
+        ctypes.memmove(src, data, len(data))
+        n, st = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._check(self._lib.hdlz_compress_stream_dyn(self._ctx, src, len(data), out, cap, ctypes.byref(n), ctypes.byref(st)))
+        if st.value:
+            raise StreamError(st.value)
+        return ctypes.string_at(out, n.value)
+
     def decompress(self, data, max_out=None, flags=0):
         """Inflate one zlib stream.  `max_out=None` grows the buffer until it fits (< 2^LMAX)."""
         data = bytes(data)

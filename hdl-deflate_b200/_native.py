@@ -31,6 +31,7 @@ SIGNATURES = {
     "hdlz_get_tree": (cint, [vp, c_u8p, c_u8p]),
     "hdlz_train_tree": (cint, [vp, c_u8p, u64, c_u32p, u32, u64, vp]),
     "hdlz_compress_bound_tree": (u32, [vp, u32]),
+    "hdlz_compress_stream_dyn": (cint, [vp, c_u8p, u32, c_u8p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
     "hdlz_tree_lengths": (cint, [c_u64p, cint, cint, c_u8p]),
     "hdlz_tree_header": (cint, [c_u8p, c_u8p, cint, c_u8p, u32, ctypes.POINTER(u32)]),
     "hdlz_compress_batch": (cint, [vp, c_u8p, u64, c_u32p, u32, c_u8p, u64, c_u32p, c_u32p, u64, vp]),

@@ -382,4 +382,57 @@ int hdlz_train_tree(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, cons
     return install_tree(ctx, lit, dist);
 }
 
+int hdlz_compress_stream_dyn(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                             uint32_t *out_len, uint32_t *status)
+{
+    if (!ctx) return set_error(HDLZ_ERR_INVALID, "null context");
+    DeviceGuard guard;
+    HDLZ_CUDA(guard.enter(ctx->device));
+    if (!in || !out || !out_len) return set_error(HDLZ_ERR_INVALID, "null buffer");
+    if (len >= (1u << HDLZ_LMAX)) return set_error(HDLZ_ERR_INVALID, "stream longer than 2^LMAX");
+    if (ctx->window != HDLZ_CWINDOW) return set_error(HDLZ_ERR_INVALID, "a stream's own tree needs the FAST compressor (CWINDOW = 32)");
+    *out_len = 0;
+    // the context's own setting comes back afterwards
+    const bool had_tree = ctx->tree_set;
+    uint8_t old_lit[286], old_dist[30];
+    memcpy(old_lit, ctx->tree_lit, 286);
+    memcpy(old_dist, ctx->tree_dist, 30);
+    cudaStream_t s = ctx->stream;
+    const size_t in_slot = ((size_t)len + 15) & ~(size_t)15;
+    int rc;
+    if ((rc = grow_device((void **)&ctx->d_in, &ctx->d_in_cap, in_slot + 16))) return rc;
+    HDLZ_CUDA(cudaMemcpyAsync(ctx->d_in, in, len, cudaMemcpyHostToDevice, s));
+    // the stream's statistics: the parse of its 2 KiB blocks (a block's first position and the window at its start
+    // differ from the stream's own parse — a few symbols in 2048 — and every symbol keeps a code anyway)
+    const uint64_t nblk = len / 2048;
+    if (nblk) rc = hdlz_train_tree(ctx, ctx->d_in, 2048, nullptr, 2048, nblk, s);
+    else ctx->tree_set = false;
+    if (!rc) {
+        const size_t out_slot = ctx->tree_set ? tree_bound(ctx, len) : compress_bound(len, ctx->container);
+        rc = grow_device((void **)&ctx->d_out, &ctx->d_out_cap, out_slot);
+        if (!rc) rc = grow_device((void **)&ctx->d_meta, &ctx->d_meta_cap, 3 * sizeof(uint32_t));
+        if (!rc) rc = hdlz_compress_batch(ctx, ctx->d_in, in_slot ? in_slot : 16, nullptr, len, ctx->d_out, out_slot,
+                                          ctx->d_meta + 1, ctx->d_meta + 2, 1, s);
+        uint32_t meta[2] = {0, 0};
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(meta, ctx->d_meta + 1, sizeof meta, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "result read-back");
+        }
+        if (!rc) {
+            uint32_t st = meta[1];
+            if (st == HDLZ_OK && meta[0] > out_cap) st = HDLZ_ST_OUT_OVERFLOW;
+            if (st == HDLZ_OK) {
+                cudaError_t e = cudaMemcpyAsync(out, ctx->d_out, meta[0], cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+                if (e != cudaSuccess) rc = cuda_fail(e, "stream read-back");
+                else *out_len = meta[0];
+            }
+            if (status) *status = st;
+        }
+    }
+    const int rc2 = had_tree ? install_tree(ctx, old_lit, old_dist) : (ctx->tree_set = false, HDLZ_SUCCESS);
+    return rc ? rc : rc2;
+}
+
 }  // extern "C"

@@ -149,6 +149,14 @@ int hdlz_get_tree(hdlz_ctx *ctx, uint8_t *lit_len, uint8_t *dist_len);
 int hdlz_train_tree(hdlz_ctx *ctx, const uint8_t *d_in, uint64_t in_stride, const uint32_t *d_in_len,
                     uint32_t uniform_len, uint64_t n, void *stream);
 uint32_t hdlz_compress_bound_tree(hdlz_ctx *ctx, uint32_t len);
+/* One stream coded with ITS OWN tree — the dynamic-tree compression the reference leaves to future work
+ * (README.md:65 "HDL-Deflate compressed output is always using a static tree"): the symbols of the parse of the
+ * stream's 2 KiB blocks are counted on the GPU, the optimal length-limited code is built and the stream is coded
+ * with it in one BTYPE = 10 block (tokens: deflate.py's parse of the whole stream, as always).  Streams shorter than
+ * 2 KiB use the fixed code.  The context's own tree setting is restored before the call returns.  Arguments and
+ * status as hdlz_compress_stream; out_cap >= hdlz_compress_bound(len) + 300 always suffices. */
+int hdlz_compress_stream_dyn(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
+                             uint32_t *out_len, uint32_t *status);
 /* Device-independent helpers for an application that gathers its own statistics: optimal code lengths
  * (<= max_bits) for `n` symbol counts (0 = unused symbol, gets length 0), and the bytes every stream of a
  * context with these lengths starts with (container header, BFINAL / BTYPE = 10, RFC 1951 3.2.7 code

@@ -182,3 +182,37 @@ def test_long_stream_with_a_tree(eng):
     with pytest.raises(hz.StreamError) as e:
         eng.compress(bytes(bad))
     assert e.value.status == 11
+
+
+def test_stream_with_its_own_tree(eng):
+    """hdlz_compress_stream_dyn: the statistics of the stream's own 2 KiB blocks, one BTYPE = 10 block, the
+    reference's tokens; the context's tree setting is untouched afterwards; short streams keep the fixed code."""
+    rnd = random.Random(25)
+    data = b"".join(text_blocks(rnd, 1, 150001, b"the quick brown fox\n"))
+    nblk = len(data) // 2048
+    wl, wd = T.train([data[2048 * i:2048 * (i + 1)] for i in range(nblk)])
+    got = eng.compress_dynamic(data)
+    st, want = T.compress(data, wl, wd)
+    assert st == 0 and got == want and zlib.decompress(got) == data
+    assert (got[2] >> 1) & 3 == 2                          # BTYPE = 10
+    assert len(got) < 0.75 * len(O.compress(data)[1])
+    assert eng.tree is None
+    assert eng.decompress(got, flags=hz.F_VERIFY_ADLER) == data
+    # a few blocks only (the one-warp kernel), bytes outside the trained blocks' alphabet in the tail
+    small = data[:5000] + bytes(range(256))
+    wl, wd = T.train([small[:2048], small[2048:4096]])
+    got = eng.compress_dynamic(small)
+    assert got == T.compress(small, wl, wd)[1] and zlib.decompress(got) == small
+    # shorter than one block: the fixed code
+    assert eng.compress_dynamic(b"a" * 12).hex() == "789c4b8483c444001d9a048d"
+    with pytest.raises(hz.StreamError) as e:               # isize < 5: the engine never starts, as in every mode
+        eng.compress_dynamic(b"abcd")
+    assert e.value.status == 1                             # HDLZ_ST_SHORT_INPUT
+    # an installed tree survives the call
+    lit, dist = eng.train_tree(np.frombuffer(data[:4096], dtype=np.uint8).reshape(2, 2048))
+    eng.compress_dynamic(data[:30000])
+    assert eng.tree is not None and list(eng.tree[0]) == list(lit) and list(eng.tree[1]) == list(dist)
+    # other containers
+    eng.set_tree()
+    eng.container = hz.CONTAINER_GZIP
+    assert zlib.decompress(eng.compress_dynamic(data[:40000]), 31) == data[:40000]
