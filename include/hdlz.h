@@ -154,7 +154,9 @@ uint32_t hdlz_compress_bound_tree(hdlz_ctx *ctx, uint32_t len);
  * stream's 2 KiB blocks are counted on the GPU, the optimal length-limited code is built and the stream is coded
  * with it in one BTYPE = 10 block (tokens: deflate.py's parse of the whole stream, as always).  Streams shorter than
  * 2 KiB use the fixed code.  The context's own tree setting is restored before the call returns.  Arguments and
- * status as hdlz_compress_stream; out_cap >= hdlz_compress_bound(len) + 300 always suffices. */
+ * status as hdlz_compress_stream.  out_cap >= hdlz_compress_bound(len) + 8192 always suffices (code description, the
+ * +1 counts, and up to 2047 tail bytes outside the counted blocks at 15 bits each); a smaller out_cap that the stream
+ * does not fit gives HDLZ_ST_OUT_OVERFLOW, never an overrun. */
 int hdlz_compress_stream_dyn(hdlz_ctx *ctx, const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap,
                              uint32_t *out_len, uint32_t *status);
 /* Device-independent helpers for an application that gathers its own statistics: optimal code lengths
